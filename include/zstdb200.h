@@ -1,0 +1,173 @@
+/*
+ * zstdb200.h -- C ABI of the B200-native Zstandard block codec (libzstdb200.so).
+ *
+ * Two layers are exported, both plain C (pointers + sizes, no torch / C++ types):
+ *
+ *  (1) the libzstd entry points that luben/zstd-jni's JNI glue binds for the hot path
+ *      (SURVEY.md section 8b).  Signatures, ownership and the error convention are those of
+ *      the reference's src/main/native/zstd.h, so the unmodified jni_*.c link against this
+ *      library instead of the bundled libzstd.  Each declaration cites the JNI call site it
+ *      serves (N/ = luben/zstd-jni src/main/native/).
+ *
+ *  (2) a batch API (zstdb200_*) that the same glue -- or any other host -- uses to hand
+ *      the GPU what it is good at: thousands of independent <=128 KB chunks per call.
+ *      Every chunk becomes one frame, byte-identical to ZSTD_compress2(chunk, level).
+ *
+ * Error convention (N/common/error_private.h:49-54): functions return size_t; a value
+ * greater than (size_t)-ZSTD_error_maxCode is -(error code), see ZSTD_isError().
+ * There is NO CPU fallback: if no CUDA device is usable the calls fail with
+ * ZSTD_error_GENERIC (code 1) and zstdb200_last_error() says why.
+ */
+#ifndef ZSTDB200_H
+#define ZSTDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZSTDB200_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------
+ * (1) libzstd-compatible entry points
+ * ---------------------------------------------------------------------------------- */
+typedef struct ZSTD_CCtx_s ZSTD_CCtx;
+typedef struct ZSTD_DCtx_s ZSTD_DCtx;
+typedef ZSTD_CCtx ZSTD_CStream;
+typedef ZSTD_DCtx ZSTD_DStream;
+
+/* values of N/zstd.h:492-545 (ZSTD_cParameter) that the JNI glue sets on this path */
+typedef enum {
+    ZSTD_c_compressionLevel = 100,
+    ZSTD_c_windowLog = 101, ZSTD_c_hashLog = 102, ZSTD_c_chainLog = 103, ZSTD_c_searchLog = 104,
+    ZSTD_c_minMatch = 105, ZSTD_c_targetLength = 106, ZSTD_c_strategy = 107,
+    ZSTD_c_contentSizeFlag = 200,
+    ZSTD_c_checksumFlag = 201,
+    ZSTD_c_dictIDFlag = 202,
+    ZSTD_c_nbWorkers = 400
+} ZSTD_cParameter;
+typedef enum { ZSTD_reset_session_only = 1, ZSTD_reset_parameters = 2, ZSTD_reset_session_and_parameters = 3 } ZSTD_ResetDirective;
+typedef enum { ZSTD_e_continue = 0, ZSTD_e_flush = 1, ZSTD_e_end = 2 } ZSTD_EndDirective;
+typedef struct { const void* src; size_t size; size_t pos; } ZSTD_inBuffer;    /* N/zstd.h:731-735 */
+typedef struct { void* dst; size_t size; size_t pos; } ZSTD_outBuffer;         /* N/zstd.h:737-741 */
+
+#define ZSTD_CONTENTSIZE_UNKNOWN (0ULL - 1)
+#define ZSTD_CONTENTSIZE_ERROR (0ULL - 2)
+
+/* N/jni_zstd.c:573-667 (error-code getters), N/jni_fast_zstd.c (every call site checks ZSTD_isError) */
+ZSTDB200_API unsigned ZSTD_isError(size_t code);
+ZSTDB200_API const char* ZSTD_getErrorName(size_t code);
+ZSTDB200_API int ZSTD_getErrorCode(size_t code);          /* returns the positive ZSTD_ErrorCode */
+ZSTDB200_API unsigned ZSTD_versionNumber(void);           /* 10507 */
+ZSTDB200_API const char* ZSTD_versionString(void);        /* "1.5.7" */
+ZSTDB200_API int ZSTD_minCLevel(void);                    /* N/jni_zstd.c: minCompressionLevel */
+ZSTDB200_API int ZSTD_maxCLevel(void);
+ZSTDB200_API int ZSTD_defaultCLevel(void);
+
+/* N/jni_zstd.c:compressBound -> ZSTD_compressBound (N/zstd.h:249) */
+ZSTDB200_API size_t ZSTD_compressBound(size_t srcSize);
+
+/* contexts: N/jni_fast_zstd.c:253-258 (init -> ZSTD_createCCtx), :268-275 (free), :683-696 (DCtx) */
+ZSTDB200_API ZSTD_CCtx* ZSTD_createCCtx(void);
+ZSTDB200_API size_t ZSTD_freeCCtx(ZSTD_CCtx* cctx);
+ZSTDB200_API ZSTD_DCtx* ZSTD_createDCtx(void);
+ZSTDB200_API size_t ZSTD_freeDCtx(ZSTD_DCtx* dctx);
+/* N/jni_fast_zstd.c:277-318 (setLevel0/setChecksum0/setContentSize0/setDictID0), N/jni_zstd.c:349-566 */
+ZSTDB200_API size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, ZSTD_cParameter param, int value);
+ZSTDB200_API size_t ZSTD_CCtx_reset(ZSTD_CCtx* cctx, ZSTD_ResetDirective reset);   /* N/jni_fast_zstd.c:605,633 */
+ZSTDB200_API size_t ZSTD_DCtx_reset(ZSTD_DCtx* dctx, ZSTD_ResetDirective reset);   /* N/jni_fast_zstd.c:797,824 */
+ZSTDB200_API size_t ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* cctx, unsigned long long pledgedSrcSize);
+
+/* one-shot hot path:
+ *   ZSTD_compress2       <- N/jni_fast_zstd.c:607,635 (compressDirectByteBuffer0 / compressByteArray0), N/jni_zstd.c:23
+ *   ZSTD_compress        <- convenience (same frame as compress2 with a fresh ctx at `level`)
+ *   ZSTD_decompressDCtx  <- N/jni_fast_zstd.c:799,826,861,895
+ *   ZSTD_decompress      <- N/jni_zstd.c:62
+ * src/dst are caller-owned host memory borrowed for the duration of the call.
+ * Compression scope of this build: srcSize <= 128 KB per call (one block => one frame), levels whose
+ * parameters select the fast/dfast parsers (1..4, negative levels); anything else returns
+ * ZSTD_error_parameter_unsupported rather than silently producing different bytes.
+ * Decompression accepts any zstd stream without dictionary (multi-block, multi-frame, skippable, checksum). */
+ZSTDB200_API size_t ZSTD_compress2(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize);
+ZSTDB200_API size_t ZSTD_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int compressionLevel);
+ZSTDB200_API size_t ZSTD_compressCCtx(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize, int compressionLevel);
+ZSTDB200_API size_t ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize);
+ZSTDB200_API size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* src, size_t compressedSize);
+
+/* frame inspection (host-side header walks): N/jni_zstd.c:70-117 (decompressedSize / findFrameCompressedSize) */
+ZSTDB200_API unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);
+ZSTDB200_API size_t ZSTD_findFrameCompressedSize(const void* src, size_t srcSize);
+ZSTDB200_API unsigned long long ZSTD_decompressBound(const void* src, size_t srcSize);
+
+/* streaming (N/jni_outputstream_zstd.c:59-123, N/jni_inputstream_zstd.c:70-93, N/jni_fast_zstd.c:406-579).
+ * GPU semantics, documented in INTEGRATION.md: the compressor buffers up to one block and emits
+ * every block as an independent frame ("independent-frames mode": any zstd decoder reads it, but the
+ * bytes differ from the reference's single-frame stream); the decompressor buffers whole frames. */
+ZSTDB200_API ZSTD_CStream* ZSTD_createCStream(void);
+ZSTDB200_API size_t ZSTD_freeCStream(ZSTD_CStream* zcs);
+ZSTDB200_API size_t ZSTD_initCStream(ZSTD_CStream* zcs, int compressionLevel);
+ZSTDB200_API size_t ZSTD_compressStream2(ZSTD_CCtx* cctx, ZSTD_outBuffer* output, ZSTD_inBuffer* input, ZSTD_EndDirective endOp);
+ZSTDB200_API size_t ZSTD_compressStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output, ZSTD_inBuffer* input);
+ZSTDB200_API size_t ZSTD_flushStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output);
+ZSTDB200_API size_t ZSTD_endStream(ZSTD_CStream* zcs, ZSTD_outBuffer* output);
+ZSTDB200_API size_t ZSTD_CStreamInSize(void);
+ZSTDB200_API size_t ZSTD_CStreamOutSize(void);
+ZSTDB200_API ZSTD_DStream* ZSTD_createDStream(void);
+ZSTDB200_API size_t ZSTD_freeDStream(ZSTD_DStream* zds);
+ZSTDB200_API size_t ZSTD_initDStream(ZSTD_DStream* zds);
+ZSTDB200_API size_t ZSTD_decompressStream(ZSTD_DStream* zds, ZSTD_outBuffer* output, ZSTD_inBuffer* input);
+ZSTDB200_API size_t ZSTD_DStreamInSize(void);
+ZSTDB200_API size_t ZSTD_DStreamOutSize(void);
+
+/* ------------------------------------------------------------------------------------
+ * (2) batch API
+ * ---------------------------------------------------------------------------------- */
+typedef struct zstdb200_ctx_s zstdb200_ctx;
+
+/* A context owns one CUDA device's workspaces and a stream; it is not thread-safe (one per thread,
+ * like a ZSTD_CCtx, J/ZstdCompressCtx.java:31-34).  device < 0 selects the current device. */
+ZSTDB200_API zstdb200_ctx* zstdb200_create(int device);
+ZSTDB200_API void zstdb200_free(zstdb200_ctx* ctx);
+ZSTDB200_API const char* zstdb200_last_error(void);          /* thread-local text of the last CUDA/runtime failure */
+ZSTDB200_API int zstdb200_device_count(void);
+/* tuning knobs (also read from the environment at context creation):
+ *   "enc_warps_per_sm" / ZSTDB200_ENC_WARPS_PER_SM, "dec_warps_per_sm" / ZSTDB200_DEC_WARPS_PER_SM */
+ZSTDB200_API int zstdb200_set_option(zstdb200_ctx* ctx, const char* name, long long value);
+ZSTDB200_API unsigned long long zstdb200_kernel_launches(const zstdb200_ctx* ctx);   /* kernels launched so far */
+
+/* Host-memory batch calls (H2D, kernels, D2H inside the call; synchronous).
+ * compress_chunks: `src` is cut into ceil(srcSize/chunkSize) chunks (chunkSize <= 131072); chunk i becomes
+ * frame i; frames are written back to back into dst (a legal multi-frame zstd stream); frameSizes[i] receives
+ * each frame's size (or its error code); *dstSize the total.  dstCapacity >= sum of ZSTD_compressBound(chunk). */
+ZSTDB200_API size_t zstdb200_compress_chunks(zstdb200_ctx* ctx, int level, const void* src, size_t srcSize, size_t chunkSize,
+                                             void* dst, size_t dstCapacity, size_t* frameSizes, size_t* dstSize);
+/* decompress_frames: `src` holds nFrames items back to back, item i being frameSizes[i] bytes (each item = one or
+ * more whole frames); item i is regenerated at dst + sum(dstSizes[0..i-1]) with capacity dstSizes[i] (in: expected
+ * size, e.g. from ZSTD_getFrameContentSize; out: regenerated size or error code). */
+ZSTDB200_API size_t zstdb200_decompress_frames(zstdb200_ctx* ctx, const void* src, const size_t* frameSizes, size_t nFrames,
+                                               void* dst, size_t dstCapacity, size_t* dstSizes);
+/* scattered host buffers (what a JNI batch entry point would pass after pinning n arrays) */
+ZSTDB200_API size_t zstdb200_compress_batch(zstdb200_ctx* ctx, int level, size_t n, const void* const* src, const size_t* srcSize,
+                                            void* const* dst, const size_t* dstCapacity, size_t* dstSize);
+ZSTDB200_API size_t zstdb200_decompress_batch(zstdb200_ctx* ctx, size_t n, const void* const* src, const size_t* srcSize,
+                                              void* const* dst, const size_t* dstCapacity, size_t* dstSize);
+
+/* Device-memory calls (asynchronous on `stream`, a cudaStream_t passed as void*; 0 = the context's stream).
+ * All pointers are device pointers; offsets are uint64 arrays of n+1 entries (item i = [off[i], off[i+1])).
+ * compress_device writes frame i at d_slots + i*slotStride (slotStride >= ZSTD_compressBound(max chunk) + 32)
+ * and its size / error code to d_frameSizes[i]; compact_device then scans the sizes and concatenates the
+ * frames into d_out (coalesced), leaving the n+1 output offsets in d_outOffsets. */
+ZSTDB200_API size_t zstdb200_compress_device(zstdb200_ctx* ctx, int level, size_t n, const void* d_src, const uint64_t* d_srcOffsets,
+                                             void* d_slots, size_t slotStride, uint64_t* d_frameSizes, void* stream);
+ZSTDB200_API size_t zstdb200_compact_device(zstdb200_ctx* ctx, size_t n, const void* d_slots, size_t slotStride, const uint64_t* d_frameSizes,
+                                            void* d_out, uint64_t* d_outOffsets, void* stream);
+ZSTDB200_API size_t zstdb200_decompress_device(zstdb200_ctx* ctx, size_t n, const void* d_src, const uint64_t* d_srcOffsets,
+                                               void* d_dst, const uint64_t* d_dstOffsets, uint64_t* d_results, void* stream);
+ZSTDB200_API size_t zstdb200_sync(zstdb200_ctx* ctx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSTDB200_H */

@@ -1,0 +1,48 @@
+// zb_hostsim.cpp -- TEST-ONLY host instantiation (1-lane warp context) of the codec
+// templates in zstd_jni_b200/csrc/*.cuh.  It lets `pytest -m "not gpu"` exercise the
+// very source the CUDA kernels are built from on a machine without a GPU.  It is never
+// loaded by the product path (zstd_jni_b200/lib/libzstdb200.so has no CPU fallback).
+#include <cstdlib>
+#include <cstring>
+#include "../../zstd_jni_b200/csrc/zb_decode.cuh"
+#include "../../zstd_jni_b200/csrc/zb_encode.cuh"
+
+extern "C" {
+
+size_t zbh_compress_bound(size_t n) { return zb::compress_bound(n); }
+
+size_t zbh_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level) {
+    using namespace zb;
+    if (srcSize > BLOCKSIZE_MAX) return ERR(E_srcSize_wrong);
+    WarpHost w;
+    EncShared* S = (EncShared*)calloc(1, sizeof(EncShared));
+    u8* wk = (u8*)calloc(1, enc_work_bytes() + 64);
+    EncWork W = enc_work_carve(wk);
+    size_t const bound = compress_bound(srcSize);
+    u8* slot = (u8*)calloc(1, bound + 64);
+    // inputs are read with aligned 8-byte loads: give the copy slack on both sides
+    u8* in = (u8*)calloc(1, srcSize + 64);
+    memcpy(in + 16, src, srcSize);
+    size_t r = compress_frame(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level);
+    if (!isErr(r)) { if (r > dstCapacity) r = ERR(E_dstSize_tooSmall); else memcpy(dst, slot, r); }
+    free(S); free(wk); free(slot); free(in);
+    return r;
+}
+
+size_t zbh_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize) {
+    using namespace zb;
+    WarpHost w;
+    DecShared* S = (DecShared*)calloc(1, sizeof(DecShared));
+    u8* scratch = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
+    u8* in = (u8*)calloc(1, srcSize + 64);
+    memcpy(in + 16, src, srcSize);
+    u8* out = (u8*)calloc(1, dstCapacity + 64);
+    size_t const r = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch);
+    if (!isErr(r)) memcpy(dst, out + 16, r);
+    free(S); free(scratch); free(in); free(out);
+    return r;
+}
+
+size_t zbh_sizeof_dec_shared() { return sizeof(zb::DecShared); }
+size_t zbh_sizeof_enc_shared() { return sizeof(zb::EncShared); }
+}

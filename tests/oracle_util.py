@@ -1,0 +1,150 @@
+"""ctypes access to the CPU checkers (test infrastructure only).
+
+  oracle/libzso.so                 plain-C restatement ("port")
+  oracle/_ref/libzstd-oracle.so    the reference's own libzstd 1.5.7, compiled in place by oracle/Makefile
+  tests/hostsim/libzb_hostsim.so   1-lane host instantiation of the CUDA kernel source
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+ZSO_PATH = ROOT / "oracle" / "libzso.so"
+REF_PATH = ROOT / "oracle" / "_ref" / "libzstd-oracle.so"
+HOSTSIM_PATH = ROOT / "tests" / "hostsim" / "libzb_hostsim.so"
+
+ERR_MAX = (1 << 64) - 120
+_cache = {}
+
+
+def _load(path, protos):
+    if path in _cache:
+        return _cache[path]
+    if not Path(path).exists():
+        _cache[path] = None
+        return None
+    L = C.CDLL(str(path))
+    for name, res, args in protos:
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _cache[path] = L
+    return L
+
+
+def zso():
+    L = _load(ZSO_PATH, [
+        ("zso_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("zso_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+        ("zso_compressBound", C.c_size_t, [C.c_size_t]),
+        ("zso_findFrameCompressedSize", C.c_size_t, [C.c_char_p, C.c_size_t]),
+        ("zso_getFrameContentSize", C.c_ulonglong, [C.c_char_p, C.c_size_t]),
+    ])
+    if L is None:
+        raise RuntimeError(f"{ZSO_PATH} missing: run `make -C oracle` (or __graft_entry__.build())")
+    return L
+
+
+def ref():
+    """The compiled reference, or None when oracle/_ref was not built (no /root/reference)."""
+    return _load(REF_PATH, [
+        ("ZSTD_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("ZSTD_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+        ("ZSTD_compressBound", C.c_size_t, [C.c_size_t]),
+        ("ZSTD_createCCtx", C.c_void_p, []),
+        ("ZSTD_freeCCtx", C.c_size_t, [C.c_void_p]),
+        ("ZSTD_createDCtx", C.c_void_p, []),
+        ("ZSTD_freeDCtx", C.c_size_t, [C.c_void_p]),
+        ("ZSTD_CCtx_setParameter", C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+        ("ZSTD_CCtx_reset", C.c_size_t, [C.c_void_p, C.c_int]),
+        ("ZSTD_compress2", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+        ("ZSTD_decompressDCtx", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+        ("ZSTD_compressStream2", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+        ("ZSTD_versionString", C.c_char_p, []),
+    ])
+
+
+def hostsim():
+    L = _load(HOSTSIM_PATH, [
+        ("zbh_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("zbh_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+        ("zbh_compress_bound", C.c_size_t, [C.c_size_t]),
+    ])
+    if L is None:
+        raise RuntimeError(f"{HOSTSIM_PATH} missing: run __graft_entry__.build()")
+    return L
+
+
+def _call_c(fn, data: bytes, level=None):
+    cap = len(data) + (len(data) >> 8) + 1024
+    out = C.create_string_buffer(cap)
+    n = fn(out, cap, data, len(data), level) if level is not None else fn(out, cap, data, len(data))
+    return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
+
+
+def _call_d(fn, frame: bytes, cap: int):
+    out = C.create_string_buffer(max(cap, 1))
+    n = fn(out, cap, frame, len(frame))
+    return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
+
+
+def oracle_compress(data: bytes, level: int = 3):
+    """Frame (bytes) or negative error code, from the plain-C restatement."""
+    return _call_c(zso().zso_compress, data, level)
+
+
+def oracle_decompress(frame: bytes, cap: int):
+    return _call_d(zso().zso_decompress, frame, cap)
+
+
+def ref_compress(data: bytes, level: int = 3):
+    return _call_c(ref().ZSTD_compress, data, level)
+
+
+def ref_decompress(frame: bytes, cap: int):
+    return _call_d(ref().ZSTD_decompress, frame, cap)
+
+
+def hostsim_compress(data: bytes, level: int = 3):
+    return _call_c(hostsim().zbh_compress, data, level)
+
+
+def hostsim_decompress(frame: bytes, cap: int):
+    return _call_d(hostsim().zbh_decompress, frame, cap)
+
+
+def ref_stream_compress(data: bytes, level: int, slice_size: int = 131072, checksum: bool = False) -> bytes:
+    """The reference's streaming path (what ZstdOutputStream drives): ZSTD_compressStream2 fed `slice_size`
+    pieces then ZSTD_e_end; produces one multi-block frame with unknown content size."""
+    R = ref()
+
+    class Buf(C.Structure):
+        _fields_ = [("p", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+    cctx = R.ZSTD_createCCtx()
+    R.ZSTD_CCtx_setParameter(cctx, 100, level)
+    if checksum:
+        R.ZSTD_CCtx_setParameter(cctx, 201, 1)
+    out = bytearray()
+    dst = C.create_string_buffer(1 << 18)
+    pos = 0
+    while True:
+        piece = data[pos:pos + slice_size]
+        pos += len(piece)
+        last = pos >= len(data)
+        src = C.create_string_buffer(piece, max(len(piece), 1))
+        ib = Buf(C.cast(src, C.c_void_p), len(piece), 0)
+        while True:
+            ob = Buf(C.cast(dst, C.c_void_p), len(dst), 0)
+            r = R.ZSTD_compressStream2(cctx, C.byref(ob), C.byref(ib), 2 if last else 0)
+            assert r <= ERR_MAX, r
+            out += dst.raw[:ob.pos]
+            if (last and r == 0) or (not last and ib.pos == ib.size):
+                break
+        if last:
+            break
+    R.ZSTD_freeCCtx(cctx)
+    return bytes(out)

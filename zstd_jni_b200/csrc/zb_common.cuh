@@ -1,0 +1,171 @@
+// zb_common.cuh -- shared definitions for the B200 Zstandard block codec.
+//
+// The codec is written as warp-cooperative __host__ __device__ templates over a
+// "warp context" (lane id, lane count W, sync, broadcast).  On the GPU W = 32 and
+// one warp owns one zstd frame; the host instantiation (W = 1, tests only, see
+// tests/hostsim/) runs the very same source so that format logic can be checked
+// on a machine without a GPU.  Product builds only ever launch the CUDA kernels.
+//
+// Reference behaviour being reproduced (N/ = luben/zstd-jni src/main/native/):
+// constants N/common/zstd_internal.h:90-164, error codes N/zstd_errors.h:42-78.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZB_HD __host__ __device__ __forceinline__
+#define ZB_HDN static __host__ __device__ __noinline__
+#else
+#define ZB_HD inline
+#define ZB_HDN static
+#endif
+
+namespace zb {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef int16_t i16;
+
+// ---- error convention: (size_t)-code, N/common/error_private.h:49-54
+enum : int {
+    E_GENERIC = 1, E_prefix_unknown = 10, E_frameParameter_unsupported = 14, E_frameParameter_windowTooLarge = 16,
+    E_corruption_detected = 20, E_checksum_wrong = 22, E_literals_headerWrong = 24, E_dictionary_corrupted = 30,
+    E_parameter_unsupported = 40, E_parameter_outOfBound = 42, E_tableLog_tooLarge = 44, E_maxSymbolValue_tooLarge = 46,
+    E_maxSymbolValue_tooSmall = 48, E_stage_wrong = 60, E_init_missing = 62, E_memory_allocation = 64, E_workSpace_tooSmall = 66,
+    E_dstSize_tooSmall = 70, E_srcSize_wrong = 72, E_dstBuffer_null = 74, E_maxCode = 120
+};
+ZB_HD size_t ERR(int code) { return (size_t)0 - (size_t)code; }
+ZB_HD bool isErr(size_t c) { return c > ERR(E_maxCode); }
+
+// ---- format constants
+constexpr u32 BLOCKSIZE_MAX = 1u << 17;
+constexpr u32 MINMATCH = 3;
+constexpr u32 MaxLL = 35, MaxML = 52, MaxOff = 31, DefaultMaxOff = 28;
+constexpr u32 LLFSELog = 9, MLFSELog = 9, OffFSELog = 8, LitHufLog = 11;
+constexpr u32 LONGNBSEQ = 0x7F00;
+constexpr u32 HUF_TABLELOG_MAX = 12;
+constexpr u32 MAGIC = 0xFD2FB528u;
+
+// ---- small intrinsics with host fallbacks
+ZB_HD u32 highbit32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return 31u - (u32)__clz((int)v);
+#else
+    return 31u - (u32)__builtin_clz(v);
+#endif
+}
+ZB_HD u32 ctz64(u64 v) {
+#if defined(__CUDA_ARCH__)
+    return (u32)__ffsll((long long)v) - 1u;
+#else
+    return (u32)__builtin_ctzll(v);
+#endif
+}
+ZB_HD u32 umin(u32 a, u32 b) { return a < b ? a : b; }
+ZB_HD u32 umax(u32 a, u32 b) { return a > b ? a : b; }
+
+// Unaligned little-endian loads built from aligned 8-byte words: the GPU faults on
+// misaligned wide loads, and an aligned word that holds at least one valid byte is
+// always inside the same allocation (cudaMalloc / caching allocators round to >=256 B).
+ZB_HD u64 ld_aligned64(const u8* p) { return *reinterpret_cast<const u64*>(p); }
+ZB_HD u64 load64(const u8* p) {
+    uintptr_t const a = reinterpret_cast<uintptr_t>(p);
+    u32 const sh = (u32)(a & 7) * 8;
+    const u8* const A = reinterpret_cast<const u8*>(a & ~(uintptr_t)7);
+    u64 const lo = ld_aligned64(A);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (ld_aligned64(A + 8) << (64 - sh));
+}
+// Same, but never touches the second word unless `nbytes` (1..8) needs it.
+ZB_HD u64 load64_n(const u8* p, u32 nbytes) {
+    uintptr_t const a = reinterpret_cast<uintptr_t>(p);
+    u32 const o = (u32)(a & 7);
+    const u8* const A = reinterpret_cast<const u8*>(a & ~(uintptr_t)7);
+    u64 v = ld_aligned64(A) >> (o * 8);
+    if (o + nbytes > 8) v |= ld_aligned64(A + 8) << (64 - o * 8);
+    return v;
+}
+ZB_HD u32 load32(const u8* p) { return (u32)load64_n(p, 4); }
+ZB_HD u32 load24(const u8* p) { return (u32)load64_n(p, 3) & 0xFFFFFFu; }
+ZB_HD u32 load16(const u8* p) { return (u32)load64_n(p, 2) & 0xFFFFu; }
+
+// bits [lo, lo+n) of the little-endian bit array at p; n <= 57; lo may be negative
+// (bits below 0 read as zero, mirroring the reference's zero-filled container once
+// a backward stream is exhausted, N/common/bitstream.h:344-351).
+ZB_HD u64 peek_bits(const u8* p, i64 lo, u32 n) {
+    if (n == 0) return 0;
+    if (lo < 0) {
+        i64 const miss = -lo;
+        if (miss >= (i64)n) return 0;
+        return peek_bits(p, 0, n - (u32)miss) << miss;
+    }
+    const u8* const q = p + (lo >> 3);
+    u32 const sh = (u32)(lo & 7);
+    u64 const w = load64_n(q, (sh + n + 7) >> 3);
+    return (w >> sh) & ((n >= 64) ? ~0ull : ((1ull << n) - 1));
+}
+
+// ---- per-code extra bits / base values (N/common/zstd_internal.h:119-144; OF: code == bits)
+struct CodeTables {
+    u8 LL_bits[MaxLL + 1];
+    u8 ML_bits[MaxML + 1];
+    u32 LL_base[MaxLL + 1];
+    u32 ML_base[MaxML + 1];
+    i16 LL_defaultNorm[MaxLL + 1];
+    i16 ML_defaultNorm[MaxML + 1];
+    i16 OF_defaultNorm[DefaultMaxOff + 1];
+};
+
+// One initializer shared by the __constant__ copy (device) and the host copy.
+#define ZB_CODE_TABLES_INIT { \
+    {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16}, \
+    {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16}, \
+    {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536}, \
+    {3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539}, \
+    {4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1}, \
+    {1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1}, \
+    {1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1} }
+#if defined(__CUDACC__)
+static __constant__ CodeTables c_tables = ZB_CODE_TABLES_INIT;
+#endif
+static const CodeTables h_tables = ZB_CODE_TABLES_INIT;
+#if defined(__CUDA_ARCH__)
+#define ZB_T (::zb::c_tables)
+#else
+#define ZB_T (::zb::h_tables)
+#endif
+
+// ---- warp contexts
+#if defined(__CUDACC__)
+struct WarpDev {
+    int lane;
+    static constexpr int W = 32;
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    template <class T> __device__ __forceinline__ T bcast(T v, int src = 0) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
+    __device__ __forceinline__ u32 ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
+    __device__ __forceinline__ u32 sum(u32 v) const {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ u32 max(u32 v) const {
+        for (int o = 16; o > 0; o >>= 1) { u32 t = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = t > v ? t : v; }
+        return v;
+    }
+    __device__ __forceinline__ void atomic_inc(u32* p) const { atomicAdd(p, 1u); }
+};
+#endif
+struct WarpHost {
+    int lane = 0;
+    static constexpr int W = 1;
+    void sync() const {}
+    template <class T> T bcast(T v, int = 0) const { return v; }
+    u32 ballot(bool p) const { return p ? 1u : 0u; }
+    u32 sum(u32 v) const { return v; }
+    u32 max(u32 v) const { return v; }
+    void atomic_inc(u32* p) const { ++*p; }
+};
+
+}  // namespace zb

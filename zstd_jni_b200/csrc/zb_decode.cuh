@@ -1,0 +1,643 @@
+// zb_decode.cuh -- warp-cooperative Zstandard decoder (one warp owns one item = one or
+// more concatenated frames; blocks inside a frame are decoded in order by that warp).
+//
+// What the reference does for this path (N/ = luben/zstd-jni src/main/native/):
+//   frame layer      N/decompress/zstd_decompress.c:447-551 (header), :953-1066 (frame), :1070-1169 (multi-frame)
+//   literals         N/decompress/zstd_decompress_block.c:134-340, N/decompress/huf_decompress.c:385-698
+//   sequence tables  N/decompress/zstd_decompress_block.c:485-603,647-775, N/common/entropy_common.c:42-306
+//   decode + execute N/decompress/zstd_decompress_block.c:1001-1096,1229-1346,1615-1690
+//
+// GPU mapping (W = 32 lanes):
+//   * header / table parsing is scalar work done by lane 0 (results broadcast);
+//   * the three FSE decode tables are built by lanes 0..2 concurrently, tables live in shared memory;
+//   * the 4 Huffman streams of a literals section are decoded by lanes 0..3 concurrently;
+//   * sequences are decoded by lane 0 in batches of 32 into shared memory, then the whole warp
+//     executes them in order: every lane copies one byte per step, overlapping matches
+//     (offset < length) are copied from the already-written period so that all lanes stay independent.
+#pragma once
+#include "zb_common.cuh"
+
+namespace zb {
+
+constexpr u32 SEQ_BATCH = 32;
+
+struct DecShared {
+    u32 fse[3][512];        // [0]=LL [1]=OF [2]=ML ; nextState | nbBits<<16 | symbol<<24
+    u16 huf[1u << HUF_TABLELOG_MAX];   // symbol | nbBits<<8
+    u32 sLit[SEQ_BATCH], sMatch[SEQ_BATCH], sOff[SEQ_BATCH];
+    i16 norm[3][64];
+    u16 symNext[3][64];
+    u8 spread[3][512];
+    u8 weights[256];
+    u32 wdt[64];            // FSE decode table of the Huffman-weight stream (tableLog <= 6)
+    i16 wnorm[256];
+    u16 wnext[256];
+    u32 fseLog[3];
+    u32 fseMode[3];         // scratch between parse and build
+    u32 fseMax[3];
+    u32 hufLog;
+    u32 rep[3];
+    u32 litEntropy, fseEntropy;
+    u32 tmp[8];
+};
+
+// ------------------------------------------------------------------ NCount
+// FSE_readNCount_body, N/common/entropy_common.c:42-187, on a forward bit cursor.
+ZB_HD u32 fwd_bits(const u8* p, size_t size, size_t bitpos, u32 n) {
+    size_t const byte = bitpos >> 3;
+    if (byte >= size) return 0;
+    u32 const sh = (u32)(bitpos & 7);
+    size_t const availBytes = size - byte;
+    u32 need = (sh + n + 7) >> 3;
+    if (need > availBytes) need = (u32)availBytes;
+    u64 w = load64_n(p + byte, need);
+    if (need < 8) w &= (1ull << (need * 8)) - 1;
+    return (u32)((w >> sh) & ((1ull << n) - 1));
+}
+
+ZB_HDN size_t read_ncount(i16* norm, u32* maxSV, u32* tableLog, const u8* src, size_t srcSize) {
+    size_t bitpos = 0;
+    u32 const maxSV1 = *maxSV + 1;
+    u32 charnum = 0;
+    int nbBits, remaining, threshold, previous0 = 0;
+    if (srcSize == 0) return ERR(E_srcSize_wrong);
+    for (u32 s = 0; s < maxSV1; s++) norm[s] = 0;
+    nbBits = (int)fwd_bits(src, srcSize, bitpos, 4) + 5; bitpos += 4;
+    if (nbBits > 15) return ERR(E_tableLog_tooLarge);
+    *tableLog = (u32)nbBits;
+    remaining = (1 << nbBits) + 1;
+    threshold = 1 << nbBits;
+    nbBits++;
+    for (;;) {
+        if (previous0) {
+            for (;;) {
+                u32 const r = fwd_bits(src, srcSize, bitpos, 2); bitpos += 2;
+                charnum += r;
+                if (r != 3) break;
+            }
+            if (charnum >= maxSV1) break;
+        }
+        {   int const max = (2 * threshold - 1) - remaining;
+            int count;
+            u32 const bs = fwd_bits(src, srcSize, bitpos, (u32)nbBits);
+            if ((int)(bs & (u32)(threshold - 1)) < max) { count = (int)(bs & (u32)(threshold - 1)); bitpos += (u32)nbBits - 1; }
+            else { count = (int)(bs & (u32)(2 * threshold - 1)); if (count >= threshold) count -= max; bitpos += (u32)nbBits; }
+            count--;
+            if (count >= 0) remaining -= count; else remaining += count;
+            norm[charnum++] = (i16)count;
+            previous0 = !count;
+            if (remaining < threshold) {
+                if (remaining <= 1) break;
+                nbBits = (int)highbit32((u32)remaining) + 1;
+                threshold = 1 << (nbBits - 1);
+            }
+            if (charnum >= maxSV1) break;
+        }
+    }
+    if (remaining != 1) return ERR(E_corruption_detected);
+    if (charnum > maxSV1) return ERR(E_maxSymbolValue_tooSmall);
+    *maxSV = charnum - 1;
+    size_t const used = (bitpos + 7) >> 3;
+    if (used > srcSize) return ERR(E_corruption_detected);
+    return used;
+}
+
+// ------------------------------------------------------- FSE decode tables
+// Symbol spreading + state numbering shared by the sequence tables
+// (ZSTD_buildFSETable_body, zstd_decompress_block.c:485-603) and the Huffman-weight
+// table (FSE_buildDTable_internal, N/common/fse_decompress.c:58-159).
+// Writes packed entries nextState | nbBits<<16 | symbol<<24.  Returns false when the
+// distribution does not tile the table (reference: ERROR(GENERIC) / assert).
+ZB_HDN bool build_fse_dtable(u32* table, const i16* norm, u32 maxSV, u32 tableLog, u16* symNext, u8* spread) {
+    u32 const tableSize = 1u << tableLog, mask = tableSize - 1;
+    u32 const step = (tableSize >> 1) + (tableSize >> 3) + 3;
+    u32 high = tableSize - 1, pos = 0;
+    for (u32 s = 0; s <= maxSV; s++) {
+        if (norm[s] == -1) { spread[high--] = (u8)s; symNext[s] = 1; }
+        else symNext[s] = (u16)norm[s];
+    }
+    for (u32 s = 0; s <= maxSV; s++) {
+        int const n = norm[s];
+        for (int i = 0; i < n; i++) {
+            spread[pos] = (u8)s;
+            pos = (pos + step) & mask;
+            while (pos > high) pos = (pos + step) & mask;
+        }
+    }
+    if (pos != 0) return false;
+    for (u32 u = 0; u < tableSize; u++) {
+        u32 const s = spread[u];
+        u32 const ns = symNext[s]++;
+        u32 const nb = tableLog - highbit32(ns);
+        table[u] = (((ns << nb) - tableSize) & 0xFFFFu) | (nb << 16) | (s << 24);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------- Huffman table
+// HUF_readStats_body (entropy_common.c:243-306) + HUF_readDTableX1_wksp (huf_decompress.c:385-519).
+// Lane 0 parses the weights; the table fill is spread over the warp.
+// Returns header bytes consumed, or an error.  S.huf / S.hufLog are the result.
+template <class C>
+ZB_HDN size_t huf_read_table(const C& w, DecShared& S, const u8* src, size_t srcSize) {
+    size_t result = 0;
+    if (w.lane == 0) {
+        u8* const wt = S.weights;
+        size_t iSize, oSize = 0;
+        result = 0;
+        do {
+            if (!srcSize) { result = ERR(E_srcSize_wrong); break; }
+            iSize = src[0];
+            if (iSize >= 128) {
+                oSize = iSize - 127; iSize = (oSize + 1) / 2;
+                if (iSize + 1 > srcSize) { result = ERR(E_srcSize_wrong); break; }
+                for (size_t n = 0; n < oSize; n += 2) { u8 const b = src[1 + n / 2]; wt[n] = b >> 4; wt[n + 1] = b & 15; }
+            } else {
+                if (iSize + 1 > srcSize) { result = ERR(E_srcSize_wrong); break; }
+                // FSE_decompress_wksp_body, fse_decompress.c:243-289, two interleaved states :173-236
+                i16* const norm = S.wnorm; u32 maxSV = 255; u32 tableLog;
+                size_t const h = read_ncount(norm, &maxSV, &tableLog, src + 1, iSize);
+                if (isErr(h)) { result = h; break; }
+                if (tableLog > 6) { result = ERR(E_tableLog_tooLarge); break; }
+                u32* const dt = S.wdt;
+                if (!build_fse_dtable(dt, norm, maxSV, tableLog, S.wnext, S.spread[0])) { result = ERR(E_GENERIC); break; }
+                const u8* const bs = src + 1 + h; size_t const bsSize = iSize - h;
+                if (bsSize < 1) { result = ERR(E_srcSize_wrong); break; }
+                if (bs[bsSize - 1] == 0) { result = ERR(E_GENERIC); break; }
+                i64 pos = (i64)(bsSize - 1) * 8 + highbit32(bs[bsSize - 1]);
+                pos -= tableLog; u32 s1 = (u32)peek_bits(bs, pos, tableLog);
+                pos -= tableLog; u32 s2 = (u32)peek_bits(bs, pos, tableLog);
+                if (pos < 0) { result = ERR(E_corruption_detected); break; }
+                size_t n = 0; bool bad = false;
+                for (;;) {
+                    if (n + 2 > 255) { bad = true; break; }
+                    { u32 const e = dt[s1]; wt[n++] = (u8)(e >> 24); u32 const nb = (e >> 16) & 0xFF; pos -= nb; s1 = (e & 0xFFFF) + (u32)peek_bits(bs, pos, nb); }
+                    if (pos < 0) { wt[n++] = (u8)(dt[s2] >> 24); break; }
+                    if (n + 2 > 255) { bad = true; break; }
+                    { u32 const e = dt[s2]; wt[n++] = (u8)(e >> 24); u32 const nb = (e >> 16) & 0xFF; pos -= nb; s2 = (e & 0xFFFF) + (u32)peek_bits(bs, pos, nb); }
+                    if (pos < 0) { wt[n++] = (u8)(dt[s1] >> 24); break; }
+                }
+                if (bad) { result = ERR(E_dstSize_tooSmall); break; }
+                oSize = n;
+            }
+            // rank statistics and implied last weight (:276-301)
+            u32* const rank = S.tmp;   // ranks 1..12 packed into S.norm[1] region below
+            u16* const rk = S.symNext[1];
+            for (u32 r = 0; r <= HUF_TABLELOG_MAX + 1; r++) rk[r] = 0;
+            u32 total = 0; bool bad = false;
+            for (size_t n = 0; n < oSize; n++) { if (wt[n] > HUF_TABLELOG_MAX) { bad = true; break; } rk[wt[n]]++; total += (1u << wt[n]) >> 1; }
+            if (bad || total == 0) { result = ERR(E_corruption_detected); break; }
+            u32 const tableLog = highbit32(total) + 1;
+            if (tableLog > HUF_TABLELOG_MAX) { result = ERR(E_corruption_detected); break; }
+            u32 const rest = (1u << tableLog) - total;
+            if ((1u << highbit32(rest)) != rest) { result = ERR(E_corruption_detected); break; }
+            u32 const last = highbit32(rest) + 1;
+            wt[oSize] = (u8)last; rk[last]++;
+            if (rk[1] < 2 || (rk[1] & 1)) { result = ERR(E_corruption_detected); break; }
+            // start cell of each symbol: weights ascending, symbols ascending inside a weight
+            u16* const start = S.symNext[2];        // per-rank running start
+            u32 posc = 0;
+            for (u32 r = 1; r <= tableLog; r++) { start[r] = (u16)posc; posc += (u32)rk[r] << (r - 1); }
+            u16* const symStart = reinterpret_cast<u16*>(S.spread[1]);   // 256 x u16 = 512 B
+            for (size_t s = 0; s <= oSize; s++) {
+                u32 const ww = wt[s];
+                if (ww) { symStart[s] = start[ww]; start[ww] = (u16)(start[ww] + (1u << (ww - 1))); } else symStart[s] = 0;
+            }
+            S.hufLog = tableLog;
+            rank[0] = (u32)oSize + 1;   // number of symbols
+            result = iSize + 1;
+        } while (0);
+    }
+    w.sync();
+    result = w.bcast(result);
+    if (isErr(result)) return result;
+    {   // cooperative fill
+        u32 const nSym = S.tmp[0], tableLog = S.hufLog;
+        const u16* const symStart = reinterpret_cast<const u16*>(S.spread[1]);
+        for (u32 s = 0; s < nSym; s++) {
+            u32 const ww = S.weights[s];
+            if (!ww) continue;
+            u32 const len = 1u << (ww - 1), st = symStart[s];
+            u16 const e = (u16)(s | ((tableLog + 1 - ww) << 8));
+            for (u32 u = (u32)w.lane; u < len; u += C::W) S.huf[st + u] = e;
+        }
+    }
+    w.sync();
+    return result;
+}
+
+// one backward Huffman stream -> n symbols at dst (HUF_decompress1X1_usingDTable_internal_body :574-595)
+ZB_HDN bool huf_decode_stream(const u16* table, u32 log, const u8* src, size_t srcSize, u8* dst, size_t n) {
+    if (srcSize < 1) return false;
+    u8 const lastByte = src[srcSize - 1];
+    if (lastByte == 0) return false;
+    i64 pos = (i64)(srcSize - 1) * 8 + highbit32(lastByte);
+    size_t i = 0;
+    u32 const mask = (1u << log) - 1;
+    while (i < n) {
+        // up to 4 symbols per refill: 57-bit window just below `pos`
+        u64 const win = peek_bits(src, pos - 57, 57);
+        u32 used = 0;
+        for (int k = 0; k < 4 && i < n; k++) {
+            u32 const idx = (u32)(win >> (57 - used - log)) & mask;
+            u16 const e = table[idx];
+            dst[i++] = (u8)e;
+            used += e >> 8;
+        }
+        pos -= used;
+    }
+    return pos == 0;
+}
+
+// ------------------------------------------------------- literals section
+// ZSTD_decodeLiteralsBlock, zstd_decompress_block.c:134-340.
+// On success: *litPtr/*litSize describe the literals; returns section size.
+template <class C>
+ZB_HDN size_t decode_literals(const C& w, DecShared& S, const u8* src, size_t srcSize, size_t blockSizeMax, size_t dstCapacity,
+                              u8* scratch, const u8** litPtr, size_t* litSizeOut) {
+    size_t const expectedWrite = blockSizeMax < dstCapacity ? blockSizeMax : dstCapacity;
+    if (srcSize < 2) return ERR(E_corruption_detected);
+    u32 const b0 = src[0], type = b0 & 3, lhl = (b0 >> 2) & 3;
+    if (type == 3 && !S.litEntropy) return ERR(E_dictionary_corrupted);
+    if (type >= 2) {
+        if (srcSize < 5) return ERR(E_corruption_detected);
+        u32 const lhc = load32(src);
+        size_t lhSize, litSize, litCSize; bool single = false;
+        switch (lhl) {
+        case 0: case 1: default: single = !lhl; lhSize = 3; litSize = (lhc >> 4) & 0x3FF; litCSize = (lhc >> 14) & 0x3FF; break;
+        case 2: lhSize = 4; litSize = (lhc >> 4) & 0x3FFF; litCSize = lhc >> 18; break;
+        case 3: lhSize = 5; litSize = (lhc >> 4) & 0x3FFFF; litCSize = (lhc >> 22) + ((size_t)src[4] << 10); break;
+        }
+        if (litSize > blockSizeMax) return ERR(E_corruption_detected);
+        if (!single && litSize < 6) return ERR(E_literals_headerWrong);
+        if (litCSize + lhSize > srcSize) return ERR(E_corruption_detected);
+        if (expectedWrite < litSize) return ERR(E_dstSize_tooSmall);
+        const u8* p = src + lhSize; size_t c = litCSize;
+        if (type == 2) {
+            if (!single && (litSize == 0 || c == 0)) return ERR(E_corruption_detected);
+            size_t const h = huf_read_table(w, S, p, c);
+            if (isErr(h)) return ERR(E_corruption_detected);
+            if (h >= c) return ERR(E_corruption_detected);
+            p += h; c -= h;
+        }
+        // stream geometry (HUF_decompress4X1_usingDTable_internal_body :601-650)
+        bool ok = true;
+        size_t len[4], outN[4]; const u8* sp[4]; size_t seg = 0; int nStreams = 1;
+        if (single) { sp[0] = p; len[0] = c; outN[0] = litSize; }
+        else {
+            nStreams = 4;
+            if (c < 10 || litSize < 6) return ERR(E_corruption_detected);
+            size_t const l1 = load16(p), l2 = load16(p + 2), l3 = load16(p + 4);
+            if (l1 + l2 + l3 + 6 > c) return ERR(E_corruption_detected);
+            seg = (litSize + 3) / 4;
+            if (3 * seg > litSize) return ERR(E_corruption_detected);
+            sp[0] = p + 6; sp[1] = sp[0] + l1; sp[2] = sp[1] + l2; sp[3] = sp[2] + l3;
+            len[0] = l1; len[1] = l2; len[2] = l3; len[3] = c - (l1 + l2 + l3 + 6);
+            outN[0] = outN[1] = outN[2] = seg; outN[3] = litSize - 3 * seg;
+        }
+        // lanes 0..3 decode one stream each (all of them on a 1-lane host context)
+        for (int k = w.lane; k < nStreams; k += C::W)
+            ok = huf_decode_stream(S.huf, S.hufLog, sp[k], len[k], scratch + (size_t)k * seg, outN[k]) && ok;
+        bool const allOk = (w.ballot(!ok) == 0);
+        w.sync();
+        if (!allOk) return ERR(E_corruption_detected);
+        S.litEntropy = 1;
+        *litPtr = scratch; *litSizeOut = litSize;
+        return litCSize + lhSize;
+    }
+    size_t lhSize, litSize;
+    switch (lhl) {
+    case 0: case 2: default: lhSize = 1; litSize = b0 >> 3; break;
+    case 1: lhSize = 2; litSize = load16(src) >> 4; break;
+    case 3: lhSize = 3; if (srcSize < 3) return ERR(E_corruption_detected); litSize = load24(src) >> 4; break;
+    }
+    if (type == 1) {
+        if (lhl == 1 && srcSize < 3) return ERR(E_corruption_detected);
+        if (lhl == 3 && srcSize < 4) return ERR(E_corruption_detected);
+    }
+    if (litSize > blockSizeMax) return ERR(E_corruption_detected);
+    if (expectedWrite < litSize) return ERR(E_dstSize_tooSmall);
+    if (type == 0) {
+        if (litSize + lhSize > srcSize) return ERR(E_corruption_detected);
+        *litPtr = src + lhSize; *litSizeOut = litSize;
+        return lhSize + litSize;
+    }
+    {   u8 const v = src[lhSize];
+        for (size_t k = (size_t)w.lane; k < litSize; k += C::W) scratch[k] = v;
+        w.sync();
+    }
+    *litPtr = scratch; *litSizeOut = litSize;
+    return lhSize + 1;
+}
+
+// --------------------------------------------------- one compressed block
+// ZSTD_decompressBlock_internal :2066-2174.  `frameStart` is the first output byte of
+// the frame (offsets may reach back that far); writes at op, at most `cap` bytes.
+template <class C>
+ZB_HDN size_t decode_block(const C& w, DecShared& S, const u8* frameStart, u8* op0, size_t cap,
+                           const u8* src, size_t srcSize, size_t blockSizeMax, u8* scratch) {
+    if (srcSize > blockSizeMax) return ERR(E_srcSize_wrong);
+    const u8* ip = src; size_t left = srcSize;
+    const u8* lit = nullptr; size_t litSize = 0;
+    {   size_t const r = decode_literals(w, S, ip, left, blockSizeMax, cap, scratch, &lit, &litSize);
+        if (isErr(r)) return r;
+        ip += r; left -= r;
+    }
+    // sequences header (ZSTD_decodeSeqHeaders :695-775): lane 0 parses, lanes 0..2 build
+    size_t hdr = 0; int nbSeq = 0;
+    if (w.lane == 0) {
+        do {
+            const u8* p = ip; size_t l = left;
+            if (l < 1) { hdr = ERR(E_srcSize_wrong); break; }
+            nbSeq = *p++; l--;
+            if (nbSeq > 0x7F) {
+                if (nbSeq == 0xFF) { if (l < 2) { hdr = ERR(E_srcSize_wrong); break; } nbSeq = (int)load16(p) + (int)LONGNBSEQ; p += 2; l -= 2; }
+                else { if (l < 1) { hdr = ERR(E_srcSize_wrong); break; } nbSeq = ((nbSeq - 0x80) << 8) + *p++; l--; }
+            }
+            if (nbSeq == 0) { if (l != 0) hdr = ERR(E_corruption_detected); else hdr = (size_t)(p - ip); break; }
+            if (l < 1) { hdr = ERR(E_srcSize_wrong); break; }
+            u32 const modes = *p++; l--;
+            if (modes & 3) { hdr = ERR(E_corruption_detected); break; }
+            u32 const type[3] = { modes >> 6, (modes >> 4) & 3, (modes >> 2) & 3 };
+            u32 const maxSym[3] = { MaxLL, MaxOff, MaxML }, maxLog[3] = { LLFSELog, OffFSELog, MLFSELog };
+            bool fail = false;
+            for (int t = 0; t < 3 && !fail; t++) {
+                S.fseMode[t] = type[t];
+                switch (type[t]) {
+                case 1:   // rle
+                    if (!l) { hdr = ERR(E_corruption_detected); fail = true; break; }
+                    if (*p > maxSym[t]) { hdr = ERR(E_corruption_detected); fail = true; break; }
+                    S.fseMax[t] = *p; p++; l--; break;
+                case 0: break;
+                case 3: if (!S.fseEntropy) { hdr = ERR(E_corruption_detected); fail = true; } break;
+                default: {
+                    u32 m = maxSym[t], tl;
+                    size_t const h = read_ncount(S.norm[t], &m, &tl, p, l);
+                    if (isErr(h) || tl > maxLog[t]) { hdr = ERR(E_corruption_detected); fail = true; break; }
+                    S.fseMax[t] = m; S.fseLog[t] = tl; p += h; l -= h; } break;
+                }
+            }
+            if (fail) break;
+            hdr = (size_t)(p - ip);
+        } while (0);
+    }
+    w.sync();
+    hdr = w.bcast(hdr); nbSeq = w.bcast(nbSeq);
+    if (isErr(hdr)) return hdr;
+    ip += hdr; left -= hdr;
+    if (nbSeq) {
+        if (cap == 0) return ERR(E_dstSize_tooSmall);
+        // table construction: one lane per table (ZSTD_buildSeqTable :647-693)
+        for (int t = w.lane; t < 3; t += C::W) {
+            u32 const mode = S.fseMode[t];
+            if (mode == 1) { S.fse[t][0] = (S.fseMax[t] << 24); S.fseLog[t] = 0; }
+            else if (mode == 0) {
+                const i16* dn = t == 0 ? ZB_T.LL_defaultNorm : t == 1 ? ZB_T.OF_defaultNorm : ZB_T.ML_defaultNorm;
+                u32 const dmax = t == 0 ? MaxLL : t == 1 ? DefaultMaxOff : MaxML, dlog = t == 1 ? 5 : 6;
+                for (u32 s = 0; s <= dmax; s++) S.norm[t][s] = dn[s];
+                build_fse_dtable(S.fse[t], S.norm[t], dmax, dlog, S.symNext[t], S.spread[t]);
+                S.fseLog[t] = dlog;
+            } else if (mode == 2) {
+                build_fse_dtable(S.fse[t], S.norm[t], S.fseMax[t], S.fseLog[t], S.symNext[t], S.spread[t]);
+            }
+        }
+        w.sync();
+    }
+
+    u8* op = op0; u8* const oend = op0 + (cap < blockSizeMax ? cap : blockSizeMax);
+    const u8* const litEnd = lit + litSize;
+    size_t err = 0;
+    if (nbSeq) {
+        S.fseEntropy = 1;
+        if (left < 1 || ip[left - 1] == 0) return ERR(E_corruption_detected);
+        // lane-0 decoder state (registers of lane 0 only)
+        i64 pos = (i64)(left - 1) * 8 + highbit32(ip[left - 1]);
+        u32 sLL = 0, sOF = 0, sML = 0, rep0 = S.rep[0], rep1 = S.rep[1], rep2 = S.rep[2];
+        u32 const logLL = S.fseLog[0], logOF = S.fseLog[1], logML = S.fseLog[2];
+        if (w.lane == 0) {
+            pos -= logLL; sLL = (u32)peek_bits(ip, pos, logLL);
+            pos -= logOF; sOF = (u32)peek_bits(ip, pos, logOF);
+            pos -= logML; sML = (u32)peek_bits(ip, pos, logML);
+        }
+        int remaining = nbSeq;
+        while (remaining > 0) {
+            int const cnt = remaining < (int)SEQ_BATCH ? remaining : (int)SEQ_BATCH;
+            if (w.lane == 0) {
+                for (int k = 0; k < cnt; k++) {
+                    u32 const eLL = S.fse[0][sLL], eOF = S.fse[1][sOF], eML = S.fse[2][sML];
+                    u32 const llc = eLL >> 24, ofc = eOF >> 24, mlc = eML >> 24;
+                    u32 const llBits = ZB_T.LL_bits[llc], mlBits = ZB_T.ML_bits[mlc], ofBits = ofc;
+                    u32 litLength = ZB_T.LL_base[llc], matchLength = ZB_T.ML_base[mlc], offset;
+                    if (ofBits > 1) {
+                        pos -= ofBits;
+                        offset = ((1u << ofBits) - 3) + (u32)peek_bits(ip, pos, ofBits);
+                        rep2 = rep1; rep1 = rep0; rep0 = offset;
+                    } else {
+                        u32 const ll0 = (litLength == 0);
+                        if (ofBits == 0) {
+                            offset = ll0 ? rep1 : rep0;
+                            rep1 = ll0 ? rep0 : rep1; rep0 = offset;
+                        } else {
+                            pos -= 1;
+                            u32 const idx = 1 + ll0 + (u32)peek_bits(ip, pos, 1);
+                            u32 temp = (idx == 3) ? rep0 - 1 : (idx == 1 ? rep1 : rep2);
+                            temp -= !temp;
+                            if (idx != 1) rep2 = rep1;
+                            rep1 = rep0; rep0 = temp; offset = temp;
+                        }
+                    }
+                    {   u32 const nb = mlBits + llBits;
+                        pos -= nb;
+                        u32 const x = (u32)peek_bits(ip, pos, nb);
+                        matchLength += x >> llBits;
+                        litLength += x & ((1u << llBits) - 1);
+                    }
+                    if (remaining - k > 1) {
+                        u32 const nLL = (eLL >> 16) & 0xFF, nML = (eML >> 16) & 0xFF, nOF = (eOF >> 16) & 0xFF;
+                        u32 const nb = nLL + nML + nOF;
+                        pos -= nb;
+                        u32 const y = (u32)peek_bits(ip, pos, nb);
+                        sLL = (eLL & 0xFFFF) + (y >> (nML + nOF));
+                        sML = (eML & 0xFFFF) + ((y >> nOF) & ((1u << nML) - 1));
+                        sOF = (eOF & 0xFFFF) + (y & ((1u << nOF) - 1));
+                    }
+                    S.sLit[k] = litLength; S.sMatch[k] = matchLength; S.sOff[k] = offset;
+                }
+            }
+            w.sync();
+            // execute the batch, in order (ZSTD_execSequence :1001-1096 / _End :905-948)
+            for (int k = 0; k < cnt; k++) {
+                size_t const ll = S.sLit[k], ml = S.sMatch[k], off = S.sOff[k];
+                if (ll + ml > (size_t)(oend - op)) { err = ERR(E_dstSize_tooSmall); break; }
+                if (ll > (size_t)(litEnd - lit)) { err = ERR(E_corruption_detected); break; }
+                for (size_t j = (size_t)w.lane; j < ll; j += C::W) op[j] = lit[j];
+                op += ll; lit += ll;
+                if (off > (size_t)(op - frameStart)) { err = ERR(E_corruption_detected); break; }
+                w.sync();
+                const u8* const m = op - off;
+                if (off >= ml) { for (size_t j = (size_t)w.lane; j < ml; j += C::W) op[j] = m[j]; }
+                else if (C::W == 1) { for (size_t j = 0; j < ml; j++) op[j] = m[j]; }
+                else { for (size_t j = (size_t)w.lane; j < ml; j += C::W) op[j] = m[j % off]; }
+                op += ml;
+                w.sync();
+            }
+            if (err) break;
+            remaining -= cnt;
+            w.sync();
+        }
+        if (err) return err;
+        bool bad = false;
+        if (w.lane == 0) { bad = (pos != 0); S.rep[0] = rep0; S.rep[1] = rep1; S.rep[2] = rep2; }
+        bad = w.bcast((u32)bad) != 0;
+        w.sync();
+        if (bad) return ERR(E_corruption_detected);
+    }
+    {   size_t const last = (size_t)(litEnd - lit);
+        if (last > (size_t)(oend - op)) return ERR(E_dstSize_tooSmall);
+        for (size_t j = (size_t)w.lane; j < last; j += C::W) op[j] = lit[j];
+        op += last;
+        w.sync();
+    }
+    return (size_t)(op - op0);
+}
+
+// ---------------------------------------------------------------- XXH64
+// published xxHash64 (N/common/xxhash.h), serial; only used when the frame asks for it.
+ZB_HD u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+ZB_HDN u64 xxh64(const u8* p, size_t len) {
+    constexpr u64 P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
+    const u8* const end = p + len; u64 h;
+    auto rnd = [&](u64 acc, u64 in) { acc += in * P2; acc = rotl64(acc, 31); return acc * P1; };
+    auto mrg = [&](u64 acc, u64 v) { v = rnd(0, v); acc ^= v; return acc * P1 + P4; };
+    if (len >= 32) {
+        u64 v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
+        do { v1 = rnd(v1, load64(p)); v2 = rnd(v2, load64(p + 8)); v3 = rnd(v3, load64(p + 16)); v4 = rnd(v4, load64(p + 24)); p += 32; } while (p + 32 <= end);
+        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h = mrg(h, v1); h = mrg(h, v2); h = mrg(h, v3); h = mrg(h, v4);
+    } else h = P5;
+    h += (u64)len;
+    while (p + 8 <= end) { h ^= rnd(0, load64_n(p, 8)); h = rotl64(h, 27) * P1 + P4; p += 8; }
+    if (p + 4 <= end) { h ^= (u64)load32(p) * P1; h = rotl64(h, 23) * P2 + P3; p += 4; }
+    while (p < end) { h ^= (*p++) * P5; h = rotl64(h, 11) * P1; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
+// ------------------------------------------------------------ frame layer
+struct FrameHeader { u32 headerSize; u64 contentSize; u64 windowSize; u32 blockSizeMax; u32 checksum, skippable, skipLen, hasContentSize; };
+
+// ZSTD_getFrameHeader_advanced :447-551.  0 = ok, >0 = bytes wanted, or error
+ZB_HDN size_t read_frame_header(FrameHeader* fh, const u8* src, size_t srcSize) {
+    fh->headerSize = 0; fh->contentSize = 0; fh->windowSize = 0; fh->blockSizeMax = 0;
+    fh->checksum = fh->skippable = fh->skipLen = 0; fh->hasContentSize = 0;
+    if (srcSize < 5) {
+        if (srcSize > 0) {
+            u32 const k = (u32)(srcSize < 4 ? srcSize : 4);
+            u32 got = 0; for (u32 i = 0; i < k; i++) got |= (u32)src[i] << (8 * i);
+            u32 const m = (k == 4) ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1);
+            if ((got & m) != (MAGIC & m)) {
+                if ((got & m & 0xFFFFFFF0u) != (0x184D2A50u & m & 0xFFFFFFF0u)) return ERR(E_prefix_unknown);
+            }
+        }
+        return 5;
+    }
+    u32 const magic = load32(src);
+    if (magic != MAGIC) {
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
+            if (srcSize < 8) return 8;
+            fh->skippable = 1; fh->skipLen = load32(src + 4); fh->headerSize = 8;
+            return 0;
+        }
+        return ERR(E_prefix_unknown);
+    }
+    u32 const fhd = src[4], dictID = fhd & 3, single = (fhd >> 5) & 1, fcsID = fhd >> 6;
+    u32 const didSize = dictID == 3 ? 4 : dictID, fcsSize = fcsID == 0 ? 0 : (1u << fcsID);
+    size_t const hs = 5 + !single + didSize + fcsSize + (single && !fcsID);
+    if (srcSize < hs) return hs;
+    fh->headerSize = (u32)hs;
+    if (fhd & 0x08) return ERR(E_frameParameter_unsupported);
+    size_t pos = 5;
+    if (!single) {
+        u32 const wl = src[pos++], windowLog = (wl >> 3) + 10;
+        if (windowLog > 31) return ERR(E_frameParameter_windowTooLarge);
+        fh->windowSize = 1ull << windowLog; fh->windowSize += (fh->windowSize >> 3) * (wl & 7);
+    }
+    pos += didSize;
+    fh->hasContentSize = 1;
+    switch (fcsID) {
+    case 0: if (single) fh->contentSize = src[pos]; else fh->hasContentSize = 0; break;
+    case 1: fh->contentSize = (u64)load16(src + pos) + 256; break;
+    case 2: fh->contentSize = load32(src + pos); break;
+    default: fh->contentSize = load64_n(src + pos, 8); break;
+    }
+    if (single) fh->windowSize = fh->contentSize;
+    fh->blockSizeMax = (u32)(fh->windowSize < BLOCKSIZE_MAX ? fh->windowSize : BLOCKSIZE_MAX);
+    fh->checksum = (fhd >> 2) & 1;
+    return 0;
+}
+
+// ZSTD_decompressMultiFrame :1070-1169 + ZSTD_decompressFrame :953-1066.
+// Uniform across the warp; returns regenerated size or an error code.
+template <class C>
+ZB_HDN size_t decompress_item(const C& w, DecShared& S, const u8* src, size_t srcSize, u8* dst, size_t dstCapacity, u8* scratch) {
+    size_t total = 0; bool more = false;
+    while (srcSize >= 4) {
+        if (srcSize >= 8 && (load32(src) & 0xFFFFFFF0u) == 0x184D2A50u) {
+            size_t const skip = 8 + (size_t)load32(src + 4);
+            if (skip > srcSize) return ERR(E_srcSize_wrong);
+            src += skip; srcSize -= skip; continue;
+        }
+        // ---- one frame
+        if (srcSize < 6 + 3) return ERR(E_srcSize_wrong);
+        FrameHeader fh;
+        {   size_t const r = read_frame_header(&fh, src, srcSize);
+            if (isErr(r)) return (more && r == ERR(E_prefix_unknown)) ? ERR(E_srcSize_wrong) : r;
+            if (r > 0) return ERR(E_srcSize_wrong);
+            if (srcSize < fh.headerSize + 3) return ERR(E_srcSize_wrong);
+        }
+        const u8* ip = src + fh.headerSize; size_t left = srcSize - fh.headerSize;
+        if (w.lane == 0) { S.rep[0] = 1; S.rep[1] = 4; S.rep[2] = 8; S.litEntropy = 0; S.fseEntropy = 0; }
+        w.sync();
+        size_t written = 0;
+        for (;;) {
+            if (left < 3) return ERR(E_srcSize_wrong);
+            u32 const bh = load24(ip), type = (bh >> 1) & 3; size_t cSize = bh >> 3;
+            if (type == 3) return ERR(E_corruption_detected);
+            if (type == 1) cSize = 1;
+            ip += 3; left -= 3;
+            if (cSize > left) return ERR(E_srcSize_wrong);
+            size_t decoded;
+            if (type == 2) {
+                decoded = decode_block(w, S, dst, dst + written, dstCapacity - written, ip, cSize, fh.blockSizeMax, scratch);
+                if (isErr(decoded)) return decoded;
+            } else if (type == 0) {
+                if (cSize > dstCapacity - written) return ERR(E_dstSize_tooSmall);
+                for (size_t j = (size_t)w.lane; j < cSize; j += C::W) dst[written + j] = ip[j];
+                decoded = cSize; w.sync();
+            } else {
+                size_t const rl = bh >> 3;
+                if (rl > dstCapacity - written) return ERR(E_dstSize_tooSmall);
+                u8 const v = *ip;
+                for (size_t j = (size_t)w.lane; j < rl; j += C::W) dst[written + j] = v;
+                decoded = rl; w.sync();
+            }
+            written += decoded; ip += cSize; left -= cSize;
+            if (bh & 1) break;
+        }
+        if (fh.hasContentSize && written != fh.contentSize) return ERR(E_corruption_detected);
+        if (fh.checksum) {
+            if (left < 4) return ERR(E_checksum_wrong);
+            u32 calc = 0;
+            if (w.lane == 0) calc = (u32)xxh64(dst, written);
+            calc = w.bcast(calc);
+            if (calc != load32(ip)) return ERR(E_checksum_wrong);
+            ip += 4; left -= 4;
+        }
+        dst += written; dstCapacity -= written; total += written; more = true;
+        src = ip; srcSize = left;
+    }
+    if (srcSize) return ERR(E_srcSize_wrong);
+    return total;
+}
+
+}  // namespace zb

@@ -1,0 +1,1002 @@
+// zb_encode.cuh -- warp-cooperative one-shot Zstandard frame encoder for inputs of at
+// most one block (<= 128 KB): the unit of work of the batch API.  The emitted frame is
+// byte-identical to the reference's ZSTD_compress2(chunk, level) (levels whose
+// parameters select the dfast or fast parser at these sizes, i.e. 1..4 and negatives).
+//
+// Reference decisions being reproduced (N/ = luben/zstd-jni src/main/native/):
+//   parameters     N/compress/clevels.h:78-130, N/compress/zstd_compress.c:1472-1609,7759-7782
+//   framing        N/compress/zstd_compress.c:4591-4743,5344-5381
+//   parsers        N/compress/zstd_double_fast.c:105-323 (dfast), N/compress/zstd_fast.c:190-423 (fast)
+//   literals       N/compress/zstd_compress_literals.c:129-235, N/compress/huf_compress.c:146-1434, N/compress/hist.c
+//   sequences      N/compress/zstd_compress.c:2693-3042, N/compress/zstd_compress_sequences.c:156-382,
+//                  N/compress/fse_compress.c:68-525
+//
+// GPU mapping (W = 32 lanes, one warp per frame):
+//   * the greedy parse is inherently sequential (every table write feeds later reads), so lane 0
+//     walks the block; hash tables live in a per-warp global workspace that stays L2-resident;
+//   * literal gathering, histograms, code computation, Huffman stream sizing run on all lanes;
+//   * Huffman tree / FSE normalisation / table descriptions are tiny scalar jobs on lane 0 in shared memory;
+//   * the four Huffman streams are emitted by lanes 0..3 at offsets known from the sizing pass.
+#pragma once
+#include "zb_common.cuh"
+
+namespace zb {
+
+struct CParams { u32 windowLog, chainLog, hashLog, searchLog, minMatch, targetLength, strategy; };
+enum : u32 { S_fast = 1, S_dfast = 2 };
+
+constexpr u32 MAX_SEQ = (BLOCKSIZE_MAX / 4) + 8;
+constexpr u32 ENC_HASHLOG_MAX = 17;     // largest hashLog / chainLog of the supported rows
+
+// ZSTD_getCParams_internal (:7759-7782) + ZSTD_adjustCParams_internal (:1472-1609) for a known
+// srcSize <= 128 KB, no dictionary.  Returns false when the level selects a parser this build lacks.
+ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize) {
+    // rows 0..4 of the "<=128 KB" and "<=16 KB" tables (clevels.h:78-84,104-109)
+    const CParams t128[5] = { {17,12,12,1,5,1,S_fast}, {17,12,13,1,6,0,S_fast}, {17,13,15,1,5,0,S_fast}, {17,15,16,2,5,0,S_dfast}, {17,17,17,2,4,0,S_dfast} };
+    const CParams t16[4] = { {14,12,13,1,5,1,S_fast}, {14,14,15,1,5,0,S_fast}, {14,14,15,1,4,0,S_fast}, {14,14,15,2,4,0,S_dfast} };
+    if (srcSize > BLOCKSIZE_MAX) return false;
+    int row = level;
+    if (level == 0) row = 3;
+    if (level < 0) row = 0;
+    bool const small = srcSize <= 16 * 1024;
+    if (row > (small ? 3 : 4)) return false;
+    CParams cp = small ? t16[row] : t128[row];
+    if (level < 0) { int const l = level < -(1 << 17) ? -(1 << 17) : level; cp.targetLength = (u32)(-l); }
+    u32 const tSize = (u32)srcSize;
+    u32 const srcLog = (tSize < 64) ? 6 : highbit32(tSize - 1) + 1;
+    if (cp.windowLog > srcLog) cp.windowLog = srcLog;
+    if (cp.hashLog > cp.windowLog + 1) cp.hashLog = cp.windowLog + 1;
+    if (cp.chainLog > cp.windowLog) cp.chainLog = cp.windowLog;      // cycleLog == chainLog below btlazy2
+    if (cp.windowLog < 10) cp.windowLog = 10;
+    *out = cp;
+    return true;
+}
+
+ZB_HD size_t compress_bound(size_t n) { return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0); }
+
+// ---- per-warp global workspace (carved by the host, see zb_capi.cu)
+struct EncWork {
+    u32* hashLong;      // 1 << ENC_HASHLOG_MAX entries, zeroed by the kernel per frame (only the used part)
+    u32* hashSmall;     // 1 << ENC_HASHLOG_MAX entries
+    u32* seqLL;         // MAX_SEQ each
+    u32* seqOF;
+    u32* seqML;
+    u8* lit;            // BLOCKSIZE_MAX + 32
+    u8* codes;          // 3 * MAX_SEQ
+};
+ZB_HD size_t enc_work_bytes() {
+    return (size_t)2 * (4u << ENC_HASHLOG_MAX) + (size_t)3 * 4 * MAX_SEQ + (BLOCKSIZE_MAX + 32) + 3 * MAX_SEQ + 64;
+}
+ZB_HD EncWork enc_work_carve(u8* base) {
+    EncWork w;
+    w.hashLong = reinterpret_cast<u32*>(base); base += (size_t)4 << ENC_HASHLOG_MAX;
+    w.hashSmall = reinterpret_cast<u32*>(base); base += (size_t)4 << ENC_HASHLOG_MAX;
+    w.seqLL = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
+    w.seqOF = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
+    w.seqML = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
+    w.lit = base; base += BLOCKSIZE_MAX + 32;
+    w.codes = base;
+    return w;
+}
+
+// ---- per-warp shared scratch
+struct HNode { u32 count; u16 parent; u8 byte; u8 nbBits; };
+struct SymTT { int deltaFindState; u32 deltaNbBits; };
+struct FseCT { u32 tableLog; u16 stateTable[512]; SymTT tt[64]; };
+struct EncShared {
+    u32 count[256];
+    HNode node[2 * 256 + 2];
+    u16 rankBase[192], rankCurr[192];
+    u8 hufBits[256]; u16 hufCode[256];
+    u8 weights[256];
+    i16 norm[64];
+    u16 cumul[66];
+    u8 tableSymbol[512];
+    FseCT ct[3];            // LL, OF, ML (ct[0] is also borrowed for the Huffman-weight table)
+    u32 streamBits[4];
+    u32 tmp[8];
+};
+
+// ---- hashing / matching (N/compress/zstd_compress_internal.h:854-945)
+ZB_HD u32 hash_ptr(const u8* p, u32 hBits, u32 mls) {
+    switch (mls) {
+    default:
+    case 4: return (load32(p) * 2654435761U) >> (32 - hBits);
+    case 5: return (u32)(((load64(p) << 24) * 889523592379ULL) >> (64 - hBits));
+    case 6: return (u32)(((load64(p) << 16) * 227718039650203ULL) >> (64 - hBits));
+    case 7: return (u32)(((load64(p) << 8) * 58295818150454627ULL) >> (64 - hBits));
+    case 8: return (u32)((load64(p) * 0xCF1BBCDCB7A56463ULL) >> (64 - hBits));
+    }
+}
+// ZSTD_count: common prefix of in[] / match[] with in bounded by end
+ZB_HD u32 count_match(const u8* in, const u8* match, const u8* end) {
+    const u8* const s = in;
+    while (in + 8 <= end) {
+        u64 const d = load64(in) ^ load64(match);
+        if (d) return (u32)(in - s) + (ctz64(d) >> 3);
+        in += 8; match += 8;
+    }
+    while (in < end && *in == *match) { in++; match++; }
+    return (u32)(in - s);
+}
+
+// ZSTD_compressBlock_doubleFast_noDict_generic, zstd_double_fast.c:105-323, for a fresh frame:
+// index = position + 2, zero cells are empty, prefixLowestIndex = 2.  Serial (call from one lane).
+// Emits sequences into W.seq* and returns their count; *lastLL gets the trailing literal run.
+ZB_HDN u32 parse_dfast(const EncWork& W, const u8* src, size_t srcSize, u32 hBitsL, u32 hBitsS, u32 mls, u32* lastLL) {
+    u32* const hashLong = W.hashLong; u32* const hashSmall = W.hashSmall;
+    const u8* const base = src - 2;
+    const u8* const iend = src + srcSize;
+    const u8* const ilimit = iend - 8;
+    const u8* const prefixLowest = src;
+    const u8* anchor = src;
+    const u8* ip = src + 1;                                  // ip += (ip == prefixLowest)
+    u32 offset_1 = 1, offset_2 = 4;                          // repStartValue {1,4,8}
+    u32 nbSeq = 0;
+    {   u32 const maxRep = 1;                                // current - windowLow at position 1
+        if (offset_2 > maxRep) offset_2 = 0;
+        if (offset_1 > maxRep) offset_1 = 0;
+    }
+    for (;;) {
+        u32 step = 1; const u8* nextStep = ip + 256; const u8* ip1 = ip + step;
+        u32 hl0, hl1 = 0, mLength, idxl0, idxl1 = 0, curr = 0, offset = 0;
+        const u8* match = nullptr;
+        int kind = 0;   // 1 = repcode at ip+1, 2 = long at ip, 3 = short at ip
+        if (ip1 > ilimit) break;
+        hl0 = hash_ptr(ip, hBitsL, 8); idxl0 = hashLong[hl0];
+        for (;;) {
+            u32 const hs0 = hash_ptr(ip, hBitsS, mls);
+            u32 const idxs0 = hashSmall[hs0];
+            curr = (u32)(ip - base);
+            hashLong[hl0] = curr; hashSmall[hs0] = curr;
+            if ((offset_1 > 0) && (load32(ip + 1 - offset_1) == load32(ip + 1))) { kind = 1; break; }
+            hl1 = hash_ptr(ip1, hBitsL, 8);
+            if (idxl0 >= 2 && load64(base + idxl0) == load64(ip)) { kind = 2; break; }
+            idxl1 = hashLong[hl1];
+            if (idxs0 >= 2 && load32(base + idxs0) == load32(ip)) { match = base + idxs0; kind = 3; break; }
+            if (ip1 >= nextStep) { step++; nextStep += 256; }
+            ip = ip1; ip1 += step;
+            hl0 = hl1; idxl0 = idxl1;
+            if (ip1 > ilimit) break;
+        }
+        if (kind == 0) break;
+        if (kind == 1) {
+            mLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
+            ip++;
+            W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = mLength; nbSeq++;
+        } else {
+            if (kind == 2) {
+                match = base + idxl0;
+                mLength = count_match(ip + 8, match + 8, iend) + 8;
+                offset = (u32)(ip - match);
+            } else {
+                mLength = count_match(ip + 4, match + 4, iend) + 4;
+                offset = (u32)(ip - match);
+                if ((idxl1 > 2) && (load64(base + idxl1) == load64(ip1))) {
+                    const u8* const matchl1 = base + idxl1;
+                    u32 const l1len = count_match(ip1 + 8, matchl1 + 8, iend) + 8;
+                    if (l1len > mLength) { ip = ip1; mLength = l1len; offset = (u32)(ip - matchl1); match = matchl1; }
+                }
+            }
+            while (((ip > anchor) & (match > prefixLowest)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+            offset_2 = offset_1; offset_1 = offset;
+            if (step < 4) hashLong[hl1] = (u32)(ip1 - base);
+            W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = offset + 3; W.seqML[nbSeq] = mLength; nbSeq++;
+        }
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            u32 const ins = curr + 2;
+            hashLong[hash_ptr(base + ins, hBitsL, 8)] = ins;
+            hashLong[hash_ptr(ip - 2, hBitsL, 8)] = (u32)(ip - 2 - base);
+            hashSmall[hash_ptr(base + ins, hBitsS, mls)] = ins;
+            hashSmall[hash_ptr(ip - 1, hBitsS, mls)] = (u32)(ip - 1 - base);
+            while ((ip <= ilimit) && (offset_2 > 0) && (load32(ip) == load32(ip - offset_2))) {
+                u32 const rLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
+                u32 const t = offset_2; offset_2 = offset_1; offset_1 = t;
+                hashSmall[hash_ptr(ip, hBitsS, mls)] = (u32)(ip - base);
+                hashLong[hash_ptr(ip, hBitsL, 8)] = (u32)(ip - base);
+                W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength; nbSeq++;
+                ip += rLength; anchor = ip;
+            }
+        }
+    }
+    *lastLL = (u32)(iend - anchor);
+    return nbSeq;
+}
+
+// ---- forward bit writer (LSB first); close appends the 1-bit end mark.
+// Mirrors BIT_CStream_t / HUF_CStream_t bounds: 8 bytes of slack are required (bitstream.h:226-242).
+struct BitW {
+    u8* p; size_t cap; size_t n; u64 acc; u32 nb;
+    ZB_HD void init(u8* dst, size_t c) { p = dst; cap = c; n = 0; acc = 0; nb = 0; }
+    ZB_HD void add(u64 v, u32 bits) {
+        if (!bits) return;
+        v &= (bits >= 64) ? ~0ull : ((1ull << bits) - 1);
+        acc |= v << nb; nb += bits;
+        while (nb >= 8) { if (n < cap) p[n] = (u8)acc; n++; acc >>= 8; nb -= 8; }
+    }
+    ZB_HD size_t flush_partial() { if (nb) { if (n < cap) p[n] = (u8)acc; n++; acc = 0; nb = 0; } return n; }
+    ZB_HD size_t close() {
+        add(1, 1);
+        if (cap <= 8 || n >= cap - 8) return 0;
+        if (nb) { p[n] = (u8)acc; return n + 1; }
+        return n;
+    }
+};
+
+// ---- warp histogram of bytes; returns largest count, trims *maxSV (HIST_count_simple, hist.c:39-74)
+template <class C>
+ZB_HDN u32 hist_warp(const C& w, u32* count, u32* maxSV, const u8* src, size_t n) {
+    u32 const m0 = *maxSV;
+    for (u32 s = (u32)w.lane; s <= m0; s += C::W) count[s] = 0;
+    w.sync();
+    if (n == 0) { *maxSV = 0; return 0; }
+    for (size_t i = (size_t)w.lane; i < n; i += C::W) w.atomic_inc(&count[src[i]]);
+    w.sync();
+    u32 largest = 0, top = 0;
+    for (u32 s = (u32)w.lane; s <= m0; s += C::W) { u32 const c = count[s]; if (c > largest) largest = c; if (c) top = s; }
+    largest = w.max(largest); top = w.max(top);
+    *maxSV = top;
+    return largest;
+}
+// scalar variant for tiny inputs handled by one lane
+ZB_HDN u32 hist_serial(u32* count, u32* maxSV, const u8* src, size_t n) {
+    u32 m = *maxSV, largest = 0;
+    for (u32 s = 0; s <= m; s++) count[s] = 0;
+    if (n == 0) { *maxSV = 0; return 0; }
+    for (size_t i = 0; i < n; i++) count[src[i]]++;
+    while (!count[m]) m--;
+    *maxSV = m;
+    for (u32 s = 0; s <= m; s++) if (count[s] > largest) largest = count[s];
+    return largest;
+}
+
+// ------------------------------------------------------------------- FSE
+// FSE_optimalTableLog_internal, fse_compress.c:348-369
+ZB_HD u32 fse_optimal_log(u32 maxTableLog, size_t srcSize, u32 maxSV, u32 minus) {
+    u32 const maxBitsSrc = highbit32((u32)(srcSize - 1)) - minus;
+    u32 tableLog = maxTableLog;
+    u32 const minBitsSrc = highbit32((u32)srcSize) + 1, minBitsSymbols = highbit32(maxSV) + 2;
+    u32 const minBits = minBitsSrc < minBitsSymbols ? minBitsSrc : minBitsSymbols;
+    if (tableLog == 0) tableLog = 11;
+    if (maxBitsSrc < tableLog) tableLog = maxBitsSrc;
+    if (minBits > tableLog) tableLog = minBits;
+    if (tableLog < 5) tableLog = 5;
+    if (tableLog > 12) tableLog = 12;
+    return tableLog;
+}
+// FSE_normalizeM2 :379-463
+ZB_HDN size_t fse_normalize_m2(i16* norm, u32 tableLog, const u32* count, size_t total, u32 maxSV, i16 lowProbCount) {
+    i16 const NOT_YET = -2; u32 distributed = 0, ToDistribute;
+    u32 const lowThreshold = (u32)(total >> tableLog);
+    u32 lowOne = (u32)((total * 3) >> (tableLog + 1));
+    for (u32 s = 0; s <= maxSV; s++) {
+        if (count[s] == 0) { norm[s] = 0; continue; }
+        if (count[s] <= lowThreshold) { norm[s] = lowProbCount; distributed++; total -= count[s]; continue; }
+        if (count[s] <= lowOne) { norm[s] = 1; distributed++; total -= count[s]; continue; }
+        norm[s] = NOT_YET;
+    }
+    ToDistribute = (1u << tableLog) - distributed;
+    if (ToDistribute == 0) return 0;
+    if ((total / ToDistribute) > lowOne) {
+        lowOne = (u32)((total * 3) / (ToDistribute * 2));
+        for (u32 s = 0; s <= maxSV; s++)
+            if ((norm[s] == NOT_YET) && (count[s] <= lowOne)) { norm[s] = 1; distributed++; total -= count[s]; }
+        ToDistribute = (1u << tableLog) - distributed;
+    }
+    if (distributed == maxSV + 1) {
+        u32 maxV = 0, maxC = 0;
+        for (u32 s = 0; s <= maxSV; s++) if (count[s] > maxC) { maxV = s; maxC = count[s]; }
+        norm[maxV] = (i16)(norm[maxV] + (i16)ToDistribute);
+        return 0;
+    }
+    if (total == 0) {
+        for (u32 s = 0; ToDistribute > 0; s = (s + 1) % (maxSV + 1))
+            if (norm[s] > 0) { ToDistribute--; norm[s]++; }
+        return 0;
+    }
+    u64 const vStepLog = 62 - tableLog;
+    u64 const mid = (1ULL << (vStepLog - 1)) - 1;
+    u64 const rStep = ((((u64)1 << vStepLog) * ToDistribute) + mid) / (u32)total;
+    u64 tmpTotal = mid;
+    for (u32 s = 0; s <= maxSV; s++) {
+        if (norm[s] == NOT_YET) {
+            u64 const end = tmpTotal + (count[s] * rStep);
+            u32 const sStart = (u32)(tmpTotal >> vStepLog), sEnd = (u32)(end >> vStepLog);
+            u32 const weight = sEnd - sStart;
+            if (weight < 1) return ERR(E_GENERIC);
+            norm[s] = (i16)weight; tmpTotal = end;
+        }
+    }
+    return 0;
+}
+// FSE_normalizeCount :465-525
+ZB_HDN size_t fse_normalize(i16* norm, u32 tableLog, const u32* count, size_t total, u32 maxSV, bool useLowProb) {
+    const u32 rtb[8] = { 0, 473195, 504333, 520860, 550000, 700000, 750000, 830000 };
+    i16 const lowProbCount = useLowProb ? -1 : 1;
+    u64 const scale = 62 - tableLog;
+    u64 const step = ((u64)1 << 62) / (u32)total;
+    u64 const vStep = 1ULL << (scale - 20);
+    int still = 1 << tableLog;
+    u32 largest = 0; i16 largestP = 0;
+    u32 const lowThreshold = (u32)(total >> tableLog);
+    if (tableLog < 5) return ERR(E_GENERIC);
+    if (tableLog > 12) return ERR(E_tableLog_tooLarge);
+    {   u32 const a = highbit32((u32)total) + 1, b = highbit32(maxSV) + 2;
+        if (tableLog < (a < b ? a : b)) return ERR(E_GENERIC); }
+    for (u32 s = 0; s <= maxSV; s++) {
+        if (count[s] == total) return 0;
+        if (count[s] == 0) { norm[s] = 0; continue; }
+        if (count[s] <= lowThreshold) { norm[s] = lowProbCount; still--; }
+        else {
+            i16 proba = (i16)((count[s] * step) >> scale);
+            if (proba < 8) { u64 const restToBeat = vStep * rtb[proba]; proba = (i16)(proba + (((count[s] * step) - ((u64)proba << scale)) > restToBeat)); }
+            if (proba > largestP) { largestP = proba; largest = s; }
+            norm[s] = proba; still -= proba;
+        }
+    }
+    if (-still >= (norm[largest] >> 1)) {
+        size_t const e = fse_normalize_m2(norm, tableLog, count, total, maxSV, lowProbCount);
+        if (isErr(e)) return e;
+    } else norm[largest] = (i16)(norm[largest] + (i16)still);
+    return tableLog;
+}
+// FSE_writeNCount_generic :233-327
+ZB_HDN size_t fse_write_ncount(u8* dst, size_t cap, const i16* norm, u32 maxSV, u32 tableLog) {
+    BitW w; w.init(dst, cap);
+    int nbBits, remaining, threshold; bool previousIs0 = false; u32 symbol = 0; u32 const alphabetSize = maxSV + 1;
+    int const tableSize = 1 << tableLog;
+    w.add(tableLog - 5, 4);
+    remaining = tableSize + 1; threshold = tableSize; nbBits = (int)tableLog + 1;
+    while ((symbol < alphabetSize) && (remaining > 1)) {
+        if (previousIs0) {
+            u32 start = symbol;
+            while ((symbol < alphabetSize) && !norm[symbol]) symbol++;
+            if (symbol == alphabetSize) break;
+            while (symbol >= start + 24) { start += 24; w.add(0xFFFF, 16); }
+            while (symbol >= start + 3) { start += 3; w.add(3, 2); }
+            w.add(symbol - start, 2);
+        }
+        int count = norm[symbol++];
+        int const max = (2 * threshold - 1) - remaining;
+        remaining -= count < 0 ? -count : count;
+        count++;
+        if (count >= threshold) count += max;
+        w.add((u64)count, (u32)(nbBits - (count < max)));
+        previousIs0 = (count == 1);
+        if (remaining < 1) return ERR(E_GENERIC);
+        while (remaining < threshold) { nbBits--; threshold >>= 1; }
+    }
+    if (remaining != 1) return ERR(E_GENERIC);
+    size_t const n = w.flush_partial();
+    if (n > cap) return ERR(E_dstSize_tooSmall);
+    return n;
+}
+// FSE_buildCTable_wksp :68-214
+ZB_HDN void fse_build_ctable(FseCT& ct, const i16* norm, u32 maxSV, u32 tableLog, u16* cumul, u8* tableSymbol) {
+    u32 const tableSize = 1u << tableLog, mask = tableSize - 1, step = (tableSize >> 1) + (tableSize >> 3) + 3;
+    u32 high = tableSize - 1, pos = 0;
+    ct.tableLog = tableLog;
+    cumul[0] = 0;
+    for (u32 u = 1; u <= maxSV + 1; u++) {
+        if (norm[u - 1] == -1) { cumul[u] = (u16)(cumul[u - 1] + 1); tableSymbol[high--] = (u8)(u - 1); }
+        else cumul[u] = (u16)(cumul[u - 1] + (u16)norm[u - 1]);
+    }
+    cumul[maxSV + 1] = (u16)(tableSize + 1);
+    for (u32 s = 0; s <= maxSV; s++) {
+        int const n = norm[s];
+        for (int i = 0; i < n; i++) {
+            tableSymbol[pos] = (u8)s;
+            pos = (pos + step) & mask;
+            while (pos > high) pos = (pos + step) & mask;
+        }
+    }
+    for (u32 u = 0; u < tableSize; u++) { u8 const sy = tableSymbol[u]; ct.stateTable[cumul[sy]++] = (u16)(tableSize + u); }
+    u32 total = 0;
+    for (u32 s = 0; s <= maxSV; s++) {
+        int const n = norm[s];
+        if (n == 0) { ct.tt[s].deltaNbBits = ((tableLog + 1) << 16) - (1u << tableLog); ct.tt[s].deltaFindState = 0; }
+        else if (n == -1 || n == 1) { ct.tt[s].deltaNbBits = (tableLog << 16) - (1u << tableLog); ct.tt[s].deltaFindState = (int)(total - 1); total++; }
+        else {
+            u32 const maxBitsOut = tableLog - highbit32((u32)n - 1);
+            u32 const minStatePlus = (u32)n << maxBitsOut;
+            ct.tt[s].deltaNbBits = (maxBitsOut << 16) - minStatePlus;
+            ct.tt[s].deltaFindState = (int)(total - (u32)n);
+            total += (u32)n;
+        }
+    }
+}
+ZB_HD void fse_build_ctable_rle(FseCT& ct, u32 symbol) { ct.tableLog = 0; ct.stateTable[0] = 0; ct.stateTable[1] = 0; ct.tt[symbol].deltaNbBits = 0; ct.tt[symbol].deltaFindState = 0; }
+// FSE_initCState2 / FSE_encodeSymbol, N/common/fse.h:428-461
+ZB_HD u32 fse_init_state2(const FseCT& ct, u32 symbol) {
+    SymTT const tt = ct.tt[symbol];
+    u32 const nbBitsOut = (tt.deltaNbBits + (1 << 15)) >> 16;
+    u32 const v = (nbBitsOut << 16) - tt.deltaNbBits;
+    return ct.stateTable[(int)(v >> nbBitsOut) + tt.deltaFindState];
+}
+ZB_HD u32 fse_encode(BitW& w, const FseCT& ct, u32 state, u32 symbol) {
+    SymTT const tt = ct.tt[symbol];
+    u32 const nbBitsOut = (state + tt.deltaNbBits) >> 16;
+    w.add(state, nbBitsOut);
+    return ct.stateTable[(int)(state >> nbBitsOut) + tt.deltaFindState];
+}
+
+// --------------------------------------------------------------- Huffman
+// HUF_sort & friends, huf_compress.c:530-665.  The quicksort is restated operation for
+// operation (with an explicit stack): the order it leaves equal counts in decides the codes.
+constexpr u32 HUF_LOG_BUCKETS_BEGIN = 158, HUF_DISTINCT_CUTOFF = 165, HUF_RANK_TABLE = 192;
+ZB_HD u32 huf_bucket(u32 count) { return count < HUF_DISTINCT_CUTOFF ? count : highbit32(count) + HUF_LOG_BUCKETS_BEGIN; }
+ZB_HD void hnode_swap(HNode* a, HNode* b) { HNode const t = *a; *a = *b; *b = t; }
+ZB_HDN void huf_insertion(HNode* a, int low, int high) {
+    int const size = high - low + 1; a += low;
+    for (int i = 1; i < size; i++) { HNode const key = a[i]; int j = i - 1; while (j >= 0 && a[j].count < key.count) { a[j + 1] = a[j]; j--; } a[j + 1] = key; }
+}
+ZB_HD int huf_partition(HNode* a, int low, int high) {
+    u32 const pivot = a[high].count; int i = low - 1;
+    for (int j = low; j < high; j++) if (a[j].count > pivot) { i++; hnode_swap(&a[i], &a[j]); }
+    hnode_swap(&a[i + 1], &a[high]);
+    return i + 1;
+}
+ZB_HDN void huf_quicksort(HNode* a, int low, int high) {
+    // HUF_simpleQuickSort recurses on the smaller side and keeps looping on the larger one.
+    // The pending loops are kept on an explicit stack (depth <= log2(256) + 1); a popped frame
+    // resumes *inside* its while loop, i.e. without re-testing the insertion-sort threshold.
+    int stLo[16], stHi[16]; int sp = 0;
+    bool enter = true;
+    for (;;) {
+        if (enter) {
+            if (high - low < 8) { huf_insertion(a, low, high); enter = false; if (sp == 0) return; sp--; low = stLo[sp]; high = stHi[sp]; continue; }
+            enter = false;
+        }
+        if (low < high) {
+            int const idx = huf_partition(a, low, high);
+            if (idx - low < high - idx) { stLo[sp] = idx + 1; stHi[sp] = high; sp++; high = idx - 1; }
+            else { stLo[sp] = low; stHi[sp] = idx - 1; sp++; low = idx + 1; }
+            enter = true;
+        } else {
+            if (sp == 0) return;
+            sp--; low = stLo[sp]; high = stHi[sp];
+        }
+    }
+}
+ZB_HDN void huf_sort(EncShared& S, const u32* count, u32 maxSV) {
+    HNode* const node = S.node + 1;
+    for (u32 n = 0; n < HUF_RANK_TABLE; n++) { S.rankBase[n] = 0; S.rankCurr[n] = 0; }
+    for (u32 n = 0; n <= maxSV; n++) S.rankBase[huf_bucket(count[n])]++;
+    for (u32 n = HUF_RANK_TABLE - 1; n > 0; n--) { S.rankBase[n - 1] = (u16)(S.rankBase[n - 1] + S.rankBase[n]); S.rankCurr[n - 1] = S.rankBase[n - 1]; }
+    for (u32 n = 0; n <= maxSV; n++) {
+        u32 const c = count[n], r = huf_bucket(c) + 1, pos = S.rankCurr[r]++;
+        node[pos].count = c; node[pos].byte = (u8)n;
+    }
+    for (u32 n = HUF_DISTINCT_CUTOFF; n < HUF_RANK_TABLE - 1; n++) {
+        int const bucketSize = (int)S.rankCurr[n] - (int)S.rankBase[n];
+        if (bucketSize > 1) huf_quicksort(node + S.rankBase[n], 0, bucketSize - 1);
+    }
+}
+// HUF_setMaxHeight :376-498
+ZB_HDN u32 huf_set_max_height(HNode* node, u32 lastNonNull, u32 target) {
+    u32 const largestBits = node[lastNonNull].nbBits;
+    if (largestBits <= target) return largestBits;
+    int totalCost = 0; u32 const baseCost = 1u << (largestBits - target); int n = (int)lastNonNull;
+    while (node[n].nbBits > target) { totalCost += (int)(baseCost - (1u << (largestBits - node[n].nbBits))); node[n].nbBits = (u8)target; n--; }
+    while (node[n].nbBits == target) --n;
+    totalCost >>= (largestBits - target);
+    u32 const noSymbol = 0xF0F0F0F0; u32 rankLast[HUF_TABLELOG_MAX + 2];
+    for (u32 r = 0; r < HUF_TABLELOG_MAX + 2; r++) rankLast[r] = noSymbol;
+    {   u32 currentNbBits = target;
+        for (int pos = n; pos >= 0; pos--) {
+            if (node[pos].nbBits >= currentNbBits) continue;
+            currentNbBits = node[pos].nbBits;
+            rankLast[target - currentNbBits] = (u32)pos;
+        } }
+    while (totalCost > 0) {
+        u32 nBitsToDecrease = highbit32((u32)totalCost) + 1;
+        for (; nBitsToDecrease > 1; nBitsToDecrease--) {
+            u32 const highPos = rankLast[nBitsToDecrease], lowPos = rankLast[nBitsToDecrease - 1];
+            if (highPos == noSymbol) continue;
+            if (lowPos == noSymbol) break;
+            u32 const highTotal = node[highPos].count, lowTotal = 2 * node[lowPos].count;
+            if (highTotal <= lowTotal) break;
+        }
+        while ((nBitsToDecrease <= HUF_TABLELOG_MAX) && (rankLast[nBitsToDecrease] == noSymbol)) nBitsToDecrease++;
+        totalCost -= 1 << (nBitsToDecrease - 1);
+        node[rankLast[nBitsToDecrease]].nbBits++;
+        if (rankLast[nBitsToDecrease - 1] == noSymbol) rankLast[nBitsToDecrease - 1] = rankLast[nBitsToDecrease];
+        if (rankLast[nBitsToDecrease] == 0) rankLast[nBitsToDecrease] = noSymbol;
+        else {
+            rankLast[nBitsToDecrease]--;
+            if (node[rankLast[nBitsToDecrease]].nbBits != target - nBitsToDecrease) rankLast[nBitsToDecrease] = noSymbol;
+        }
+    }
+    while (totalCost < 0) {
+        if (rankLast[1] == noSymbol) {
+            while (node[n].nbBits == target) n--;
+            node[n + 1].nbBits--; rankLast[1] = (u32)(n + 1); totalCost++;
+            continue;
+        }
+        node[rankLast[1] + 1].nbBits--; rankLast[1]++; totalCost++;
+    }
+    return target;
+}
+// HUF_buildCTable_wksp :755-791 (sort, HUF_buildTree :681-718, setMaxHeight, HUF_buildCTableFromTree :730-753)
+ZB_HDN u32 huf_build_ctable(EncShared& S, const u32* count, u32 maxSV, u32 maxNbBits) {
+    HNode* const node0 = S.node; HNode* const node = S.node + 1;
+    for (u32 i = 0; i < 2 * 256 + 2; i++) { node0[i].count = 0; node0[i].parent = 0; node0[i].byte = 0; node0[i].nbBits = 0; }
+    huf_sort(S, count, maxSV);
+    int nonNull = (int)maxSV;
+    while (node[nonNull].count == 0) nonNull--;
+    int lowS = nonNull, nodeNb = 256, lowN = 256; int const nodeRoot = nodeNb + lowS - 1;
+    node[nodeNb].count = node[lowS].count + node[lowS - 1].count;
+    node[lowS].parent = node[lowS - 1].parent = (u16)nodeNb;
+    nodeNb++; lowS -= 2;
+    for (int n = nodeNb; n <= nodeRoot; n++) node[n].count = 1u << 30;
+    node0[0].count = 1u << 31;
+    while (nodeNb <= nodeRoot) {
+        int const n1 = (node[lowS].count < node[lowN].count) ? lowS-- : lowN++;
+        int const n2 = (node[lowS].count < node[lowN].count) ? lowS-- : lowN++;
+        node[nodeNb].count = node[n1].count + node[n2].count;
+        node[n1].parent = node[n2].parent = (u16)nodeNb;
+        nodeNb++;
+    }
+    node[nodeRoot].nbBits = 0;
+    for (int n = nodeRoot - 1; n >= 256; n--) node[n].nbBits = (u8)(node[node[n].parent].nbBits + 1);
+    for (int n = 0; n <= nonNull; n++) node[n].nbBits = (u8)(node[node[n].parent].nbBits + 1);
+    maxNbBits = huf_set_max_height(node, (u32)nonNull, maxNbBits);
+    u16 nbPerRank[HUF_TABLELOG_MAX + 1], valPerRank[HUF_TABLELOG_MAX + 1];
+    for (u32 r = 0; r <= HUF_TABLELOG_MAX; r++) { nbPerRank[r] = 0; valPerRank[r] = 0; }
+    for (int n = 0; n <= nonNull; n++) nbPerRank[node[n].nbBits]++;
+    {   u16 min = 0;
+        for (int n = (int)maxNbBits; n > 0; n--) { valPerRank[n] = min; min = (u16)(min + nbPerRank[n]); min >>= 1; } }
+    for (u32 n = 0; n <= maxSV; n++) S.hufBits[node[n].byte] = node[n].nbBits;
+    for (u32 n = 0; n <= maxSV; n++) S.hufCode[n] = S.hufBits[n] ? valPerRank[S.hufBits[n]]++ : 0;
+    return maxNbBits;
+}
+// FSE_compress_usingCTable_generic :551-608
+ZB_HDN size_t fse_compress_2states(u8* dst, size_t cap, const u8* src, size_t srcSize, const FseCT& ct) {
+    const u8* ip = src + srcSize; BitW w; u32 s1, s2;
+    if (srcSize <= 2) return 0;
+    if (cap <= 8) return 0;
+    w.init(dst, cap);
+    if (srcSize & 1) { s1 = fse_init_state2(ct, *--ip); s2 = fse_init_state2(ct, *--ip); s1 = fse_encode(w, ct, s1, *--ip); }
+    else { s2 = fse_init_state2(ct, *--ip); s1 = fse_init_state2(ct, *--ip); }
+    srcSize -= 2;
+    if (srcSize & 2) { s2 = fse_encode(w, ct, s2, *--ip); s1 = fse_encode(w, ct, s1, *--ip); }
+    while (ip > src) {
+        s2 = fse_encode(w, ct, s2, *--ip); s1 = fse_encode(w, ct, s1, *--ip);
+        s2 = fse_encode(w, ct, s2, *--ip); s1 = fse_encode(w, ct, s1, *--ip);
+    }
+    w.add(s2, ct.tableLog); w.add(s1, ct.tableLog);
+    return w.close();
+}
+// HUF_writeCTable_wksp :248-289 (+ HUF_compressWeights :146-186); lane 0
+ZB_HDN size_t huf_write_ctable(EncShared& S, u8* dst, size_t cap, u32 maxSV, u32 huffLog) {
+    u8* const wt = S.weights;
+    for (u32 n = 0; n < maxSV; n++) wt[n] = S.hufBits[n] ? (u8)(huffLog + 1 - S.hufBits[n]) : 0;
+    if (cap < 1) return ERR(E_dstSize_tooSmall);
+    size_t hSize = 0;
+    do {   // HUF_compressWeights(dst+1, cap-1, wt, maxSV)
+        u8* const o = dst + 1; size_t const ocap = cap - 1; size_t const wtSize = maxSV;
+        if (wtSize <= 1) { hSize = 0; break; }
+        u32 cnt[HUF_TABLELOG_MAX + 1]; u32 m = HUF_TABLELOG_MAX;
+        u32 const maxCount = hist_serial(cnt, &m, wt, wtSize);
+        if (maxCount == wtSize) { hSize = 1; break; }
+        if (maxCount == 1) { hSize = 0; break; }
+        u32 const tableLog = fse_optimal_log(6, wtSize, m, 2);
+        i16 norm[HUF_TABLELOG_MAX + 1];
+        {   size_t const e = fse_normalize(norm, tableLog, cnt, wtSize, m, false); if (isErr(e)) { hSize = e; break; } }
+        size_t const h = fse_write_ncount(o, ocap, norm, m, tableLog);
+        if (isErr(h)) { hSize = h; break; }
+        fse_build_ctable(S.ct[0], norm, m, tableLog, S.cumul, S.tableSymbol);
+        size_t const c = fse_compress_2states(o + h, ocap - h, wt, wtSize, S.ct[0]);
+        if (c == 0) { hSize = 0; break; }
+        hSize = h + c;
+    } while (0);
+    if (isErr(hSize)) return hSize;
+    if ((hSize > 1) & (hSize < maxSV / 2)) { dst[0] = (u8)hSize; return hSize + 1; }
+    if (maxSV > 128) return ERR(E_GENERIC);
+    if (((maxSV + 1) / 2) + 1 > cap) return ERR(E_dstSize_tooSmall);
+    dst[0] = (u8)(128 + (maxSV - 1));
+    wt[maxSV] = 0;
+    for (u32 n = 0; n < maxSV; n += 2) dst[(n / 2) + 1] = (u8)((wt[n] << 4) + wt[n + 1]);
+    return ((maxSV + 1) / 2) + 1;
+}
+// one Huffman stream (HUF_compress1X_usingCTable_internal_body :1055-1118): last symbol first, then end mark
+ZB_HDN size_t huf_encode_stream(const EncShared& S, u8* dst, size_t cap, const u8* src, size_t n) {
+    if (cap <= 8) return 0;
+    BitW w; w.init(dst, cap);
+    for (size_t i = n; i > 0; i--) { u8 const b = src[i - 1]; w.add(S.hufCode[b], S.hufBits[b]); }
+    return w.close();
+}
+
+// ZSTD_noCompressLiterals :39-66 / ZSTD_compressRleLiteralsBlock :81-107 ; warp copy
+template <class C>
+ZB_HDN size_t lit_raw(const C& w, u8* dst, size_t cap, const u8* src, size_t n) {
+    u32 const fl = 1 + (n > 31) + (n > 4095);
+    if (n + fl > cap) return ERR(E_dstSize_tooSmall);
+    if (w.lane == 0) {
+        if (fl == 1) dst[0] = (u8)(n << 3);
+        else if (fl == 2) { u32 const v = (1 << 2) + (u32)(n << 4); dst[0] = (u8)v; dst[1] = (u8)(v >> 8); }
+        else { u32 const v = (3 << 2) + (u32)(n << 4); dst[0] = (u8)v; dst[1] = (u8)(v >> 8); dst[2] = (u8)(v >> 16); }
+    }
+    for (size_t i = (size_t)w.lane; i < n; i += C::W) dst[fl + i] = src[i];
+    w.sync();
+    return n + fl;
+}
+template <class C>
+ZB_HDN size_t lit_rle(const C& w, u8* dst, const u8* src, size_t n) {
+    u32 const fl = 1 + (n > 31) + (n > 4095);
+    if (w.lane == 0) {
+        if (fl == 1) dst[0] = (u8)(1 + (n << 3));
+        else if (fl == 2) { u32 const v = 1 + (1 << 2) + (u32)(n << 4); dst[0] = (u8)v; dst[1] = (u8)(v >> 8); }
+        else { u32 const v = 1 + (3 << 2) + (u32)(n << 4); dst[0] = (u8)v; dst[1] = (u8)(v >> 8); dst[2] = (u8)(v >> 16); }
+        dst[fl] = src[0];
+    }
+    w.sync();
+    return fl + 1;
+}
+
+// ZSTD_compressLiterals (zstd_compress_literals.c:129-235) + HUF_compress_internal (huf_compress.c:1332-1434),
+// first block of a frame (no previous Huffman table).  Uniform return value.
+template <class C>
+ZB_HDN size_t compress_literals(const C& w, EncShared& S, u8* dst, size_t cap, const u8* src, size_t n, u32 strategy, bool disableLitCompression, bool suspectUncompressible) {
+    size_t const lhSize = 3 + (n >= 1024) + (n >= 16384); bool const single = n < 256;
+    if (disableLitCompression) return lit_raw(w, dst, cap, src, n);
+    {   int const sh = (9 - (int)strategy) < 3 ? (9 - (int)strategy) : 3;
+        if (n < ((size_t)8 << sh)) return lit_raw(w, dst, cap, src, n); }
+    if (cap < lhSize + 1) return ERR(E_dstSize_tooSmall);
+    u8* const o = dst + lhSize; size_t const ocap = cap - lhSize;
+    size_t cLit = 0;   // 0 = not compressible
+    do {
+        if (!ocap) break;
+        if (suspectUncompressible && n >= 4096 * 10) {      // :1367-1379
+            u32 m1 = 255, m2 = 255; size_t largestTotal = 0;
+            largestTotal += hist_warp(w, S.count, &m1, src, 4096);
+            largestTotal += hist_warp(w, S.count, &m2, src + n - 4096, 4096);
+            if (largestTotal <= ((2 * 4096) >> 7) + 4) break;
+        }
+        u32 maxSV = 255;
+        u32 const largest = hist_warp(w, S.count, &maxSV, src, n);
+        if (largest == n) { if (w.lane == 0) o[0] = src[0]; cLit = 1; break; }
+        if (largest <= (n >> 7) + 4) break;
+        // tree + table description on lane 0
+        size_t hSize = 0; u32 huffLog = 0;
+        if (w.lane == 0) {
+            huffLog = fse_optimal_log(LitHufLog, n, maxSV, 1);     // HUF_optimalTableLog cheap path :1284-1287
+            huffLog = huf_build_ctable(S, S.count, maxSV, huffLog);
+            hSize = huf_write_ctable(S, o, ocap, maxSV, huffLog);
+        }
+        w.sync();
+        hSize = w.bcast(hSize);
+        if (isErr(hSize)) { cLit = hSize; break; }
+        if (hSize + 12ul >= n) break;
+        u8* op = o + hSize; size_t const opcap = ocap - hSize;
+        size_t total;
+        if (single) {
+            size_t c = 0;
+            if (w.lane == 0) c = huf_encode_stream(S, op, opcap, src, n);
+            c = w.bcast(c);
+            if (c == 0) break;
+            total = hSize + c;
+        } else {
+            // HUF_compress4X_usingCTable_internal :1167-1215
+            if (opcap < 6 + 1 + 1 + 1 + 8) break;
+            if (n < 12) break;
+            size_t const seg = (n + 3) / 4;
+            // sizing pass: bits of each stream, all lanes
+            u32 bits[4];
+            for (int k = 0; k < 4; k++) {
+                const u8* const s = src + (size_t)k * seg; size_t const len = (k < 3) ? seg : n - 3 * seg;
+                u32 b = 0;
+                for (size_t i = (size_t)w.lane; i < len; i += C::W) b += S.hufBits[s[i]];
+                bits[k] = w.sum(b);
+            }
+            size_t sz[4], off[4]; size_t acc = 6; bool fail = false;
+            for (int k = 0; k < 4; k++) {
+                sz[k] = ((size_t)bits[k] + 1 + 7) >> 3;
+                off[k] = acc;
+                // the reference encodes stream k into what is left of the buffer and gives up on overflow
+                size_t const capk = opcap - acc;
+                if (capk <= 8 || (((size_t)bits[k] + 1) >> 3) >= capk - 8) { fail = true; break; }
+                if (sz[k] > 65535) { fail = true; break; }
+                acc += sz[k];
+            }
+            if (fail) break;
+            for (int k = w.lane; k < 4; k += C::W) {
+                const u8* const s = src + (size_t)k * seg; size_t const len = (k < 3) ? seg : n - 3 * seg;
+                huf_encode_stream(S, op + off[k], opcap - off[k], s, len);
+                if (k < 3) { op[2 * k] = (u8)sz[k]; op[2 * k + 1] = (u8)(sz[k] >> 8); }
+            }
+            w.sync();
+            total = hSize + acc;
+        }
+        if (total >= n - 1) break;     // HUF_compressCTable_internal :1237
+        cLit = total;
+    } while (0);
+    w.sync();
+    {   size_t const minGain = (n >> 6) + 2;
+        if (cLit == 0 || isErr(cLit) || cLit >= n - minGain) return lit_raw(w, dst, cap, src, n); }
+    if (cLit == 1) {
+        // n >= 64 here, so the "single byte really is the whole literal run" check of :199-206 holds
+        return lit_rle(w, dst, src, n);
+    }
+    if (w.lane == 0) {
+        if (lhSize == 3) { u32 const lhc = 2 + ((u32)(!single) << 2) + ((u32)n << 4) + ((u32)cLit << 14); dst[0] = (u8)lhc; dst[1] = (u8)(lhc >> 8); dst[2] = (u8)(lhc >> 16); }
+        else if (lhSize == 4) { u32 const lhc = 2 + (2 << 2) + ((u32)n << 4) + ((u32)cLit << 18); dst[0] = (u8)lhc; dst[1] = (u8)(lhc >> 8); dst[2] = (u8)(lhc >> 16); dst[3] = (u8)(lhc >> 24); }
+        else { u32 const lhc = 2 + (3 << 2) + ((u32)n << 4) + ((u32)cLit << 22); dst[0] = (u8)lhc; dst[1] = (u8)(lhc >> 8); dst[2] = (u8)(lhc >> 16); dst[3] = (u8)(lhc >> 24); dst[4] = (u8)(cLit >> 10); }
+    }
+    w.sync();
+    return lhSize + cLit;
+}
+
+// ------------------------------------------------------ sequences section
+ZB_HD u32 ll_code(u32 ll) {   // ZSTD_LLcode, zstd_compress_internal.h:584-596
+    if (ll > 63) return highbit32(ll) + 19;
+    if (ll < 16) return ll;
+    // 16..63 -> 16,16,17,17,18,18,19,19,20x4,21x4,22x8,23x8,24x16
+    if (ll < 24) return 16 + ((ll - 16) >> 1);
+    if (ll < 32) return 20 + ((ll - 24) >> 2);
+    if (ll < 48) return 22 + ((ll - 32) >> 3);
+    return 24;
+}
+ZB_HD u32 ml_code(u32 mlBase) {   // ZSTD_MLcode :601-613
+    if (mlBase > 127) return highbit32(mlBase) + 36;
+    if (mlBase < 32) return mlBase;
+    // 32..127 -> 32,32,33,33,34,34,35,35,36x4,37x4,38x8,39x8,40x16,41x16,42x32
+    if (mlBase < 40) return 32 + ((mlBase - 32) >> 1);
+    if (mlBase < 48) return 36 + ((mlBase - 40) >> 2);
+    if (mlBase < 64) return 38 + ((mlBase - 48) >> 3);
+    if (mlBase < 96) return 40 + ((mlBase - 64) >> 4);
+    return 42;
+}
+// ZSTD_selectEncodingType, first block, strategy < ZSTD_lazy (zstd_compress_sequences.c:156-204,232-234)
+ZB_HD u32 select_encoding(size_t mostFrequent, size_t nbSeq, u32 defaultNormLog, bool defaultAllowed, u32 strategy) {
+    if (mostFrequent == nbSeq) return (defaultAllowed && nbSeq <= 2) ? 0 : 1;
+    if (defaultAllowed) {
+        size_t const mult = 10 - strategy;
+        size_t const dynamicFse_nbSeq_min = (((size_t)1 << defaultNormLog) * mult) >> 3;
+        if ((nbSeq < dynamicFse_nbSeq_min) || (mostFrequent < (nbSeq >> (defaultNormLog - 1)))) return 0;
+    }
+    return 2;
+}
+
+// ZSTD_entropyCompressSeqStore_internal :2887-3003 on the block body; returns body size, 0 = emit raw block
+template <class C>
+ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t cap, u32 nbSeq, size_t litSize, u32 strategy, bool disableLitCompression) {
+    u8* op = dst; u8* const oend = dst + cap;
+    {   bool const suspect = (nbSeq == 0) || (litSize / nbSeq >= 20);
+        size_t const c = compress_literals(w, S, op, cap, W.lit, litSize, strategy, disableLitCompression, suspect);
+        if (isErr(c)) return c;
+        op += c; }
+    if ((oend - op) < 3 + 1) return ERR(E_dstSize_tooSmall);
+    if (w.lane == 0) {
+        if (nbSeq < 128) op[0] = (u8)nbSeq;
+        else if (nbSeq < LONGNBSEQ) { op[0] = (u8)((nbSeq >> 8) + 0x80); op[1] = (u8)nbSeq; }
+        else { op[0] = 0xFF; op[1] = (u8)(nbSeq - LONGNBSEQ); op[2] = (u8)((nbSeq - LONGNBSEQ) >> 8); }
+    }
+    op += (nbSeq < 128) ? 1 : (nbSeq < LONGNBSEQ) ? 2 : 3;
+    if (nbSeq == 0) { w.sync(); return (size_t)(op - dst); }
+    u8* const llc = W.codes; u8* const ofc = llc + MAX_SEQ; u8* const mlc = ofc + MAX_SEQ;
+    for (u32 u = (u32)w.lane; u < nbSeq; u += C::W) {     // ZSTD_seqToCodes :2693-2719
+        llc[u] = (u8)ll_code(W.seqLL[u]);
+        ofc[u] = (u8)highbit32(W.seqOF[u]);
+        mlc[u] = (u8)ml_code(W.seqML[u] - MINMATCH);
+    }
+    w.sync();
+    u8* const seqHead = op++;
+    size_t lastCountSize = 0; u32 types[3];
+    // ZSTD_buildSequencesStatistics :2762-2880 : histogram on all lanes, table work on lane 0
+    for (int t = 0; t < 3; t++) {
+        const u8* const codes = t == 0 ? llc : t == 1 ? ofc : mlc;
+        u32 max = t == 0 ? MaxLL : t == 1 ? MaxOff : MaxML;
+        u32 const mf = hist_warp(w, S.count, &max, codes, nbSeq);
+        bool const defaultAllowed = (t != 1) || (max <= DefaultMaxOff);
+        u32 const dlog = t == 1 ? 5 : 6;
+        u32 const type = select_encoding(mf, nbSeq, dlog, defaultAllowed, strategy);
+        types[t] = type;
+        size_t c = 0;
+        if (w.lane == 0) {   // ZSTD_buildCTable, zstd_compress_sequences.c:242-288
+            size_t const capLeft = (size_t)(oend - op);
+            if (type == 1) { fse_build_ctable_rle(S.ct[t], max); if (capLeft == 0) c = ERR(E_dstSize_tooSmall); else { op[0] = codes[0]; c = 1; } }
+            else if (type == 0) {
+                const i16* dn = t == 0 ? ZB_T.LL_defaultNorm : t == 1 ? ZB_T.OF_defaultNorm : ZB_T.ML_defaultNorm;
+                u32 const dmax = t == 0 ? MaxLL : t == 1 ? DefaultMaxOff : MaxML;
+                for (u32 s = 0; s <= dmax; s++) S.norm[s] = dn[s];
+                fse_build_ctable(S.ct[t], S.norm, dmax, dlog, S.cumul, S.tableSymbol);
+                c = 0;
+            } else {
+                u32 const FSELog = t == 1 ? OffFSELog : LLFSELog;
+                size_t nbSeq_1 = nbSeq; u32 const tableLog = fse_optimal_log(FSELog, nbSeq, max, 2);
+                if (S.count[codes[nbSeq - 1]] > 1) { S.count[codes[nbSeq - 1]]--; nbSeq_1--; }
+                size_t r = fse_normalize(S.norm, tableLog, S.count, nbSeq_1, max, nbSeq_1 >= 2048);
+                if (!isErr(r)) r = fse_write_ncount(op, capLeft, S.norm, max, tableLog);
+                if (!isErr(r)) fse_build_ctable(S.ct[t], S.norm, max, tableLog, S.cumul, S.tableSymbol);
+                c = r;
+            }
+        }
+        w.sync();
+        c = w.bcast(c);
+        if (isErr(c)) return c;
+        if (type == 2) lastCountSize = c;
+        op += c;
+    }
+    size_t streamSize = 0;
+    if (w.lane == 0) {   // ZSTD_encodeSequences_body, zstd_compress_sequences.c:290-382
+        *seqHead = (u8)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
+        size_t const capLeft = (size_t)(oend - op);
+        if (capLeft <= 8) streamSize = ERR(E_dstSize_tooSmall);
+        else {
+            BitW bw; bw.init(op, capLeft);
+            const FseCT& ctLL = S.ct[0]; const FseCT& ctOF = S.ct[1]; const FseCT& ctML = S.ct[2];
+            u32 n = nbSeq - 1;
+            u32 sML = fse_init_state2(ctML, mlc[n]), sOF = fse_init_state2(ctOF, ofc[n]), sLL = fse_init_state2(ctLL, llc[n]);
+            bw.add(W.seqLL[n], ZB_T.LL_bits[llc[n]]);
+            bw.add(W.seqML[n] - MINMATCH, ZB_T.ML_bits[mlc[n]]);
+            bw.add(W.seqOF[n], ofc[n]);
+            while (n-- > 0) {
+                sOF = fse_encode(bw, ctOF, sOF, ofc[n]);
+                sML = fse_encode(bw, ctML, sML, mlc[n]);
+                sLL = fse_encode(bw, ctLL, sLL, llc[n]);
+                bw.add(W.seqLL[n], ZB_T.LL_bits[llc[n]]);
+                bw.add(W.seqML[n] - MINMATCH, ZB_T.ML_bits[mlc[n]]);
+                bw.add(W.seqOF[n], ofc[n]);
+            }
+            bw.add(sML, ctML.tableLog); bw.add(sOF, ctOF.tableLog); bw.add(sLL, ctLL.tableLog);
+            streamSize = bw.close();
+            if (streamSize == 0) streamSize = ERR(E_dstSize_tooSmall);
+        }
+    }
+    w.sync();
+    streamSize = w.bcast(streamSize);
+    if (isErr(streamSize)) return streamSize;
+    op += streamSize;
+    if (lastCountSize && (lastCountSize + streamSize) < 4) return 0;    // :2992-2998
+    return (size_t)(op - dst);
+}
+
+// ZSTD_compressBlock_fast_noDict_generic, N/compress/zstd_fast.c:190-423, fresh frame, serial.
+// The reference software-pipelines positions ip0..ip3; the order of table writes and reads
+// is observable in the output, so it is kept.
+ZB_HD bool match4(const u8* cur, const u8* base, u32 idx) { return idx >= 2 && load32(cur) == load32(base + idx); }
+ZB_HDN u32 parse_fast(const EncWork& W, const u8* src, size_t srcSize, u32 hlog, u32 mls, u32 targetLength, u32* lastLL) {
+    u32* const hashTable = W.hashLong;
+    u32 const stepSize = targetLength + !targetLength + 1;
+    const u8* const base = src - 2;
+    const u8* const prefixStart = src;
+    const u8* const iend = src + srcSize;
+    const u8* const ilimit = iend - 8;
+    const u8* anchor = src; const u8* ip0 = src + 1; const u8* ip1; const u8* ip2; const u8* ip3;
+    u32 current0 = 0, rep1 = 1, rep2 = 4, nbSeq = 0;
+    {   u32 const maxRep = 1;
+        if (rep2 > maxRep) rep2 = 0;
+        if (rep1 > maxRep) rep1 = 0; }
+    for (;;) {   // _start
+        u32 step = stepSize; const u8* nextStep = ip0 + 128;
+        u32 hash0, hash1, matchIdx, mLength = 0, offcode = 0; const u8* match0 = nullptr; int kind = 0;   // 1 = repcode, 2 = hash match
+        ip1 = ip0 + 1; ip2 = ip0 + step; ip3 = ip2 + 1;
+        if (ip3 >= ilimit) break;
+        hash0 = hash_ptr(ip0, hlog, mls); hash1 = hash_ptr(ip1, hlog, mls);
+        matchIdx = hashTable[hash0];
+        do {
+            u32 const rval = load32(ip2 - rep1);
+            current0 = (u32)(ip0 - base);
+            hashTable[hash0] = current0;
+            if ((load32(ip2) == rval) & (rep1 > 0)) {
+                ip0 = ip2; match0 = ip0 - rep1;
+                mLength = ip0[-1] == match0[-1];
+                ip0 -= mLength; match0 -= mLength;
+                offcode = 1; mLength += 4;
+                hashTable[hash1] = (u32)(ip1 - base);
+                kind = 1; break;
+            }
+            if (match4(ip0, base, matchIdx)) { hashTable[hash1] = (u32)(ip1 - base); kind = 2; break; }
+            matchIdx = hashTable[hash1];
+            hash0 = hash1; hash1 = hash_ptr(ip2, hlog, mls);
+            ip0 = ip1; ip1 = ip2; ip2 = ip3;
+            current0 = (u32)(ip0 - base);
+            hashTable[hash0] = current0;
+            if (match4(ip0, base, matchIdx)) { if (step <= 4) hashTable[hash1] = (u32)(ip1 - base); kind = 2; break; }
+            matchIdx = hashTable[hash1];
+            hash0 = hash1; hash1 = hash_ptr(ip2, hlog, mls);
+            ip0 = ip1; ip1 = ip2; ip2 = ip0 + step; ip3 = ip1 + step;
+            if (ip2 >= nextStep) { step++; nextStep += 128; }
+        } while (ip3 < ilimit);
+        if (kind == 0) break;
+        if (kind == 2) {
+            match0 = base + matchIdx;
+            rep2 = rep1; rep1 = (u32)(ip0 - match0);
+            offcode = rep1 + 3; mLength = 4;
+            while (((ip0 > anchor) & (match0 > prefixStart)) && (ip0[-1] == match0[-1])) { ip0--; match0--; mLength++; }
+        }
+        mLength += count_match(ip0 + mLength, match0 + mLength, iend);
+        W.seqLL[nbSeq] = (u32)(ip0 - anchor); W.seqOF[nbSeq] = offcode; W.seqML[nbSeq] = mLength; nbSeq++;
+        ip0 += mLength; anchor = ip0;
+        if (ip0 <= ilimit) {
+            hashTable[hash_ptr(base + current0 + 2, hlog, mls)] = current0 + 2;
+            hashTable[hash_ptr(ip0 - 2, hlog, mls)] = (u32)(ip0 - 2 - base);
+            if (rep2 > 0) {
+                while ((ip0 <= ilimit) && (load32(ip0) == load32(ip0 - rep2))) {
+                    u32 const rLength = count_match(ip0 + 4, ip0 + 4 - rep2, iend) + 4;
+                    { u32 const t = rep2; rep2 = rep1; rep1 = t; }
+                    hashTable[hash_ptr(ip0, hlog, mls)] = (u32)(ip0 - base);
+                    ip0 += rLength;
+                    W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength; nbSeq++;
+                    anchor = ip0;
+                }
+            }
+        }
+    }
+    *lastLL = (u32)(iend - anchor);
+    return nbSeq;
+}
+
+// ------------------------------------------------------------------ frame
+// One chunk -> one frame, as ZSTD_compress2 would emit it with dstCapacity = ZSTD_compressBound(srcSize).
+// `dst` must have room for compress_bound(srcSize) + 32 bytes.  Uniform return value.
+template <class C>
+ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level) {
+    CParams cp;
+    if (!get_cparams(&cp, level, srcSize)) return ERR(E_parameter_unsupported);
+    if (dstCapacity < 18) return ERR(E_dstSize_tooSmall);
+    size_t pos = 0;
+    u32 const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256);
+    if (w.lane == 0) {   // ZSTD_writeFrameHeader :4695-4743
+        dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
+        dst[4] = (u8)((1 << 5) + (fcsCode << 6));
+        if (fcsCode == 0) dst[5] = (u8)srcSize;
+        else if (fcsCode == 1) { u32 const v = (u32)srcSize - 256; dst[5] = (u8)v; dst[6] = (u8)(v >> 8); }
+        else { u32 const v = (u32)srcSize; dst[5] = (u8)v; dst[6] = (u8)(v >> 8); dst[7] = (u8)(v >> 16); dst[8] = (u8)(v >> 24); }
+    }
+    pos = 5 + (fcsCode == 0 ? 1 : fcsCode == 1 ? 2 : 4);
+    if (srcSize == 0) {   // ZSTD_writeEpilogue :5364-5372
+        if (dstCapacity - pos < 3) return ERR(E_dstSize_tooSmall);
+        if (w.lane == 0) { dst[pos] = 1; dst[pos + 1] = 0; dst[pos + 2] = 0; }
+        w.sync();
+        return pos + 3;
+    }
+    u8* const op = dst + pos; size_t const cap = dstCapacity - pos;
+    if (cap < 3 + 2 + 1) return ERR(E_dstSize_tooSmall);
+    size_t cSize = 0;
+    if (srcSize >= 7) {   // ZSTD_buildSeqStore :3273-3280
+        // fresh tables: zero the used part
+        {   u32 const nL = 1u << cp.hashLog, nS = (cp.strategy == S_dfast) ? (1u << cp.chainLog) : 0;
+            for (u32 i = (u32)w.lane; i < nL; i += C::W) W.hashLong[i] = 0;
+            for (u32 i = (u32)w.lane; i < nS; i += C::W) W.hashSmall[i] = 0;
+            w.sync(); }
+        u32 nbSeq = 0, lastLL = 0;
+        if (w.lane == 0) {
+            if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
+            else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
+        }
+        w.sync();
+        nbSeq = w.bcast(nbSeq); lastLL = w.bcast(lastLL);
+        // gather literals (ZSTD_storeSeq copies them during the parse; the result is the same buffer)
+        size_t litSize = 0;
+        {   size_t sp = 0;
+            for (u32 i = 0; i < nbSeq; i++) {
+                u32 const ll = W.seqLL[i];
+                for (u32 j = (u32)w.lane; j < ll; j += C::W) W.lit[litSize + j] = src[sp + j];
+                litSize += ll; sp += ll + W.seqML[i];
+            }
+            for (u32 j = (u32)w.lane; j < lastLL; j += C::W) W.lit[litSize + j] = src[sp + j];
+            litSize += lastLL;
+            w.sync(); }
+        bool const disableLit = (cp.strategy == S_fast && cp.targetLength > 0);   // ZSTD_literalsCompressionIsDisabled
+        cSize = entropy_compress(w, S, W, op + 3, cap - 3, nbSeq, litSize, cp.strategy, disableLit);
+        // ZSTD_entropyCompressSeqStore_wExtLitBuffer :3005-3042
+        if (cSize == ERR(E_dstSize_tooSmall) && srcSize <= cap - 3) cSize = 0;
+        if (isErr(cSize)) return cSize;
+        if (cSize) { size_t const maxCSize = srcSize - ((srcSize >> 6) + 2); if (cSize >= maxCSize) cSize = 0; }
+    }
+    if (cSize == 0) {   // ZSTD_noCompressBlock
+        if (srcSize + 3 > cap) return ERR(E_dstSize_tooSmall);
+        if (w.lane == 0) { u32 const h = 1 + (u32)(srcSize << 3); op[0] = (u8)h; op[1] = (u8)(h >> 8); op[2] = (u8)(h >> 16); }
+        for (size_t i = (size_t)w.lane; i < srcSize; i += C::W) op[3 + i] = src[i];
+        w.sync();
+        return pos + 3 + srcSize;
+    }
+    if (w.lane == 0) { u32 const h = 1 + (2 << 1) + (u32)(cSize << 3); op[0] = (u8)h; op[1] = (u8)(h >> 8); op[2] = (u8)(h >> 16); }
+    w.sync();
+    return pos + 3 + cSize;
+}
+
+}  // namespace zb

@@ -1,0 +1,467 @@
+"""Python mirror of com.github.luben.zstd's hot-path API, over the C ABI of libzstdb200.so.
+
+No JVM is available in the build image, so this module plays the role of the
+reference's Java layer (J/ = src/main/java/com/github/luben/zstd/): same class and
+method names, argument meaning and error behaviour, so that the parity tests read
+like the reference's own Scala tests (src/test/scala/Zstd.scala).  Everything here is
+plumbing: every byte is produced by the CUDA kernels behind the C ABI.
+
+  Zstd.compress / decompress / compressBound / isError / getErrorName ...  J/Zstd.java
+  ZstdCompressCtx / ZstdDecompressCtx                                      J/ZstdCompressCtx.java, J/ZstdDecompressCtx.java
+  ZstdOutputStream / ZstdInputStream                                       J/ZstdOutputStreamNoFinalizer.java, J/ZstdInputStreamNoFinalizer.java
+  ZstdException                                                            J/ZstdException.java
+plus the batch entry points (Zstd.compressBatch / decompressBatch / ZstdBatchContext)
+that a JNI maintainer would add next to them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+ZSTD_c_compressionLevel = 100
+ZSTD_c_contentSizeFlag = 200
+ZSTD_c_checksumFlag = 201
+ZSTD_c_dictIDFlag = 202
+ZSTD_e_continue, ZSTD_e_flush, ZSTD_e_end = 0, 1, 2
+BLOCK = 131072
+
+
+class ZstdException(RuntimeError):
+    """J/ZstdException.java:16-32 : carries the libzstd error code and its name."""
+
+    def __init__(self, code: int, message: str | None = None):
+        self.code = code
+        super().__init__(message if message is not None else Zstd.getErrorName(code))
+
+    def getErrorCode(self) -> int:
+        return self.code
+
+
+def _buf(b) -> tuple[C.c_void_p, int, object]:
+    """(address, length, keepalive) for bytes / bytearray / numpy uint8."""
+    if isinstance(b, np.ndarray):
+        a = np.ascontiguousarray(b, dtype=np.uint8)
+        return C.c_void_p(a.ctypes.data), a.size, a
+    if isinstance(b, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(b, dtype=np.uint8)
+        return C.c_void_p(a.ctypes.data if a.size else 0), a.size, a
+    raise TypeError(f"unsupported buffer type {type(b)}")
+
+
+class Zstd:
+    """Static facade, J/Zstd.java."""
+
+    @staticmethod
+    def isError(code: int) -> bool:                      # J/Zstd.java:isError
+        return bool(N.lib().ZSTD_isError(code & ((1 << 64) - 1)))
+
+    @staticmethod
+    def getErrorName(code: int) -> str:
+        c = code if code > N.ERROR_MAX else ((1 << 64) - abs(code)) if code else 0
+        return N.lib().ZSTD_getErrorName(c).decode()
+
+    @staticmethod
+    def getErrorCode(code: int) -> int:
+        return N.lib().ZSTD_getErrorCode(code & ((1 << 64) - 1))
+
+    @staticmethod
+    def compressBound(srcSize: int) -> int:              # J/Zstd.java:compressBound -> N/jni_zstd.c
+        return N.lib().ZSTD_compressBound(srcSize)
+
+    @staticmethod
+    def minCompressionLevel() -> int:
+        return N.lib().ZSTD_minCLevel()
+
+    @staticmethod
+    def maxCompressionLevel() -> int:
+        return N.lib().ZSTD_maxCLevel()
+
+    @staticmethod
+    def defaultCompressionLevel() -> int:
+        return N.lib().ZSTD_defaultCLevel()
+
+    @staticmethod
+    def compress(src, level: int = 3) -> bytes:          # J/Zstd.java:1137-1145
+        with ZstdCompressCtx() as ctx:
+            ctx.setLevel(level)
+            return ctx.compress(src)
+
+    @staticmethod
+    def compressInto(dst: bytearray, src, level: int = 3) -> int:   # compress(byte[] dst, byte[] src, int level) -> long
+        with ZstdCompressCtx() as ctx:
+            ctx.setLevel(level)
+            return ctx.compressByteArray(dst, 0, len(dst), src, 0, len(src), raise_on_error=False)
+
+    @staticmethod
+    def decompress(src, originalSize: int) -> bytes:     # J/Zstd.java:1417-1424
+        with ZstdDecompressCtx() as ctx:
+            return ctx.decompress(src, originalSize)
+
+    @staticmethod
+    def decompressInto(dst: bytearray, src) -> int:      # decompress(byte[] dst, byte[] src) -> long (error code, not exception)
+        with ZstdDecompressCtx() as ctx:
+            return ctx.decompressByteArray(dst, 0, len(dst), src, 0, len(src), raise_on_error=False)
+
+    @staticmethod
+    def getFrameContentSize(src) -> int:                 # J/Zstd.java:getFrameContentSize ; -1 unknown, -2 error like the C API
+        p, n, _k = _buf(src)
+        v = N.lib().ZSTD_getFrameContentSize(p, n)
+        return v if v < (1 << 63) else v - (1 << 64)
+
+    @staticmethod
+    def decompressedSize(src) -> int:                    # deprecated Java name; 0 when unknown / error
+        v = Zstd.getFrameContentSize(src)
+        return v if v >= 0 else 0
+
+    @staticmethod
+    def findFrameCompressedSize(src) -> int:
+        p, n, _k = _buf(src)
+        r = N.lib().ZSTD_findFrameCompressedSize(p, n)
+        if N.is_error(r):
+            raise ZstdException(N.error_code(r), N.lib().ZSTD_getErrorName(r).decode())
+        return r
+
+    # ---- batch entry points (new surface)
+    @staticmethod
+    def compressBatch(chunks: Sequence, level: int = 3) -> List[bytes]:
+        with ZstdBatchContext() as b:
+            return b.compressBatch(chunks, level)
+
+    @staticmethod
+    def decompressBatch(frames: Sequence, originalSizes: Sequence[int]) -> List[bytes]:
+        with ZstdBatchContext() as b:
+            return b.decompressBatch(frames, originalSizes)
+
+
+class _AutoClose:
+    """J/AutoCloseBase.java : close() is idempotent, use-after-close raises."""
+    _ptr = None
+
+    def _live(self):
+        if self._ptr is None:
+            raise RuntimeError("Closed")          # IllegalStateException("Closed") in Java
+        return self._ptr
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ZstdCompressCtx(_AutoClose):
+    """J/ZstdCompressCtx.java (subset on the hot path)."""
+
+    def __init__(self):
+        self._ptr = N.lib().ZSTD_createCCtx()
+        if not self._ptr:
+            raise MemoryError("ZSTD_createCCtx failed")
+
+    def close(self):
+        if self._ptr is not None:
+            N.lib().ZSTD_freeCCtx(self._ptr)
+            self._ptr = None
+
+    def _set(self, param: int, value: int):
+        r = N.lib().ZSTD_CCtx_setParameter(self._live(), param, value)
+        if N.is_error(r):
+            raise ZstdException(N.error_code(r), N.lib().ZSTD_getErrorName(r).decode())
+        return self
+
+    def setLevel(self, level: int):                      # :69-75
+        return self._set(ZSTD_c_compressionLevel, level)
+
+    def setChecksum(self, flag: bool):
+        return self._set(ZSTD_c_checksumFlag, int(flag))
+
+    def setContentSize(self, flag: bool):
+        return self._set(ZSTD_c_contentSizeFlag, int(flag))
+
+    def setDictID(self, flag: bool):
+        return self._set(ZSTD_c_dictIDFlag, int(flag))
+
+    def reset(self):
+        N.lib().ZSTD_CCtx_reset(self._live(), 3)
+
+    def compressByteArray(self, dst: bytearray, dstOffset: int, dstSize: int, src, srcOffset: int, srcSize: int, raise_on_error=True) -> int:
+        """:691-710 ; bounds are checked the way N/jni_fast_zstd.c:615-624 does."""
+        self._live()
+        if dstOffset < 0 or dstSize < 0 or dstOffset + dstSize > len(dst):
+            raise IndexError("dst range")
+        sp, sn, _k = _buf(src)
+        if srcOffset < 0 or srcSize < 0 or srcOffset + srcSize > sn:
+            raise IndexError("src range")
+        d = (C.c_char * len(dst)).from_buffer(dst)
+        L = N.lib()
+        L.ZSTD_CCtx_reset(self._ptr, 1)
+        r = L.ZSTD_compress2(self._ptr, C.c_void_p(C.addressof(d) + dstOffset), dstSize, C.c_void_p((sp.value or 0) + srcOffset), srcSize)
+        if N.is_error(r) and raise_on_error:
+            raise ZstdException(N.error_code(r), L.ZSTD_getErrorName(r).decode())
+        return r
+
+    def compress(self, src) -> bytes:                    # :784-792
+        _p, n, _k = _buf(src)
+        dst = bytearray(max(Zstd.compressBound(n), 1))
+        size = self.compressByteArray(dst, 0, len(dst), src, 0, n)
+        return bytes(dst[:size])
+
+
+class ZstdDecompressCtx(_AutoClose):
+    """J/ZstdDecompressCtx.java (subset on the hot path)."""
+
+    def __init__(self):
+        self._ptr = N.lib().ZSTD_createDCtx()
+        if not self._ptr:
+            raise MemoryError("ZSTD_createDCtx failed")
+
+    def close(self):
+        if self._ptr is not None:
+            N.lib().ZSTD_freeDCtx(self._ptr)
+            self._ptr = None
+
+    def decompressByteArray(self, dst: bytearray, dstOffset: int, dstSize: int, src, srcOffset: int, srcSize: int, raise_on_error=True) -> int:
+        self._live()
+        if dstOffset < 0 or dstSize < 0 or dstOffset + dstSize > len(dst):
+            raise IndexError("dst range")
+        sp, sn, _k = _buf(src)
+        if srcOffset < 0 or srcSize < 0 or srcOffset + srcSize > sn:
+            raise IndexError("src range")
+        L = N.lib()
+        L.ZSTD_DCtx_reset(self._ptr, 1)
+        if len(dst):
+            d = (C.c_char * len(dst)).from_buffer(dst)
+            dp = C.c_void_p(C.addressof(d) + dstOffset)
+        else:
+            dp = C.c_void_p(0)
+        r = L.ZSTD_decompressDCtx(self._ptr, dp, dstSize, C.c_void_p((sp.value or 0) + srcOffset), srcSize)
+        if N.is_error(r) and raise_on_error:
+            raise ZstdException(N.error_code(r), L.ZSTD_getErrorName(r).decode())
+        return r
+
+    def decompress(self, src, originalSize: int) -> bytes:      # :381-394
+        if originalSize < 0:
+            raise ZstdException(72, "Src size is incorrect")
+        dst = bytearray(originalSize)
+        _p, n, _k = _buf(src)
+        size = self.decompressByteArray(dst, 0, originalSize, src, 0, n)
+        return bytes(dst[:size])
+
+
+class ZstdBatchContext(_AutoClose):
+    """Owner of a zstdb200_ctx: GPU workspaces + stream for batch calls (one per thread)."""
+
+    def __init__(self, device: int = -1):
+        L = N.lib()
+        self._ptr = L.zstdb200_create(device)
+        if not self._ptr:
+            self._ptr = None
+            raise RuntimeError("zstdb200_create failed (no CPU fallback): " + L.zstdb200_last_error().decode())
+
+    def close(self):
+        if self._ptr is not None:
+            N.lib().zstdb200_free(self._ptr)
+            self._ptr = None
+
+    @property
+    def handle(self):
+        return self._live()
+
+    def kernelLaunches(self) -> int:
+        return N.lib().zstdb200_kernel_launches(self._live())
+
+    def setOption(self, name: str, value: int):
+        if N.lib().zstdb200_set_option(self._live(), name.encode(), value) != 0:
+            raise KeyError(name)
+
+    def _raise(self, r: int):
+        L = N.lib()
+        msg = L.ZSTD_getErrorName(r).decode()
+        extra = L.zstdb200_last_error().decode()
+        raise ZstdException(N.error_code(r), msg + (f" [{extra}]" if extra and N.error_code(r) == 1 else ""))
+
+    def compressChunks(self, src, chunkSize: int = BLOCK, level: int = 3):
+        """One contiguous buffer -> (stream bytes (numpy uint8), frame sizes (numpy uint64))."""
+        L = N.lib()
+        sp, n, _k = _buf(src)
+        nch = max(1, -(-n // chunkSize))
+        cap = sum(max(18, L.ZSTD_compressBound(min(chunkSize, n - i * chunkSize) if n else 0)) for i in range(nch)) if nch < 64 else nch * max(18, L.ZSTD_compressBound(chunkSize))
+        out = np.empty(cap, dtype=np.uint8)
+        sizes = (C.c_size_t * nch)()
+        total = C.c_size_t(0)
+        r = L.zstdb200_compress_chunks(self._live(), level, sp, n, chunkSize, C.c_void_p(out.ctypes.data), cap, sizes, C.byref(total))
+        if N.is_error(r):
+            self._raise(r)
+        return out[: total.value], np.ctypeslib.as_array(sizes).astype(np.uint64)
+
+    def decompressFrames(self, stream, frameSizes: Sequence[int], originalSizes: Sequence[int]):
+        """Packed frames -> (bytes (numpy uint8, items back to back), regenerated sizes)."""
+        L = N.lib()
+        sp, n, _k = _buf(stream)
+        k = len(frameSizes)
+        fs = (C.c_size_t * k)(*[int(x) for x in frameSizes])
+        ds = (C.c_size_t * k)(*[int(x) for x in originalSizes])
+        total = int(sum(int(x) for x in originalSizes))
+        out = np.empty(max(total, 1), dtype=np.uint8)
+        r = L.zstdb200_decompress_frames(self._live(), sp, fs, k, C.c_void_p(out.ctypes.data), total, ds)
+        sizes = np.ctypeslib.as_array(ds).astype(np.uint64)
+        if N.is_error(r):
+            self._raise(r)
+        return out[:total], sizes
+
+    def compressBatch(self, chunks: Sequence, level: int = 3, raise_on_error: bool = True):
+        L = N.lib()
+        k = len(chunks)
+        bufs = [_buf(c) for c in chunks]
+        src = (C.c_void_p * k)(*[b[0] for b in bufs])
+        ssz = (C.c_size_t * k)(*[b[1] for b in bufs])
+        outs = [np.empty(max(18, L.ZSTD_compressBound(b[1])), dtype=np.uint8) for b in bufs]
+        dst = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
+        dcap = (C.c_size_t * k)(*[o.size for o in outs])
+        dsz = (C.c_size_t * k)()
+        r = L.zstdb200_compress_batch(self._live(), level, k, src, ssz, dst, dcap, dsz)
+        if N.is_error(r) and raise_on_error:
+            self._raise(r)
+        if raise_on_error:
+            return [outs[i][: dsz[i]].tobytes() for i in range(k)]
+        return [outs[i][: dsz[i]].tobytes() if not N.is_error(dsz[i]) else -N.error_code(dsz[i]) for i in range(k)]
+
+    def decompressBatch(self, frames: Sequence, originalSizes: Sequence[int], raise_on_error: bool = True):
+        L = N.lib()
+        k = len(frames)
+        bufs = [_buf(f) for f in frames]
+        src = (C.c_void_p * k)(*[b[0] for b in bufs])
+        ssz = (C.c_size_t * k)(*[b[1] for b in bufs])
+        outs = [np.empty(max(int(s), 1), dtype=np.uint8) for s in originalSizes]
+        dst = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
+        dcap = (C.c_size_t * k)(*[int(s) for s in originalSizes])
+        dsz = (C.c_size_t * k)()
+        r = L.zstdb200_decompress_batch(self._live(), k, src, ssz, dst, dcap, dsz)
+        if N.is_error(r) and raise_on_error:
+            self._raise(r)
+        if raise_on_error:
+            return [outs[i][: dsz[i]].tobytes() for i in range(k)]
+        return [outs[i][: dsz[i]].tobytes() if not N.is_error(dsz[i]) else -N.error_code(dsz[i]) for i in range(k)]
+
+
+class ZstdOutputStream:
+    """J/ZstdOutputStreamNoFinalizer.java:83-90,400-518 over ZSTD_compressStream2.
+
+    GPU build semantics: every <=128 KB block is emitted as an independent frame
+    (see INTEGRATION.md), so the bytes are a legal zstd stream but not the
+    reference's single-frame stream."""
+
+    def __init__(self, out, level: int = 3):
+        self._out = out
+        L = N.lib()
+        self._z = L.ZSTD_createCStream()
+        L.ZSTD_initCStream(self._z, level)
+        self._dst = bytearray(L.ZSTD_CStreamOutSize())
+        self._closed = False
+
+    def _step(self, data: bytes, end_op: int):
+        L = N.lib()
+        src = np.frombuffer(data, dtype=np.uint8) if data else np.empty(0, dtype=np.uint8)
+        ib = N.InBuffer(src.ctypes.data if src.size else 0, src.size, 0)
+        d = (C.c_char * len(self._dst)).from_buffer(self._dst)
+        while True:
+            ob = N.OutBuffer(C.addressof(d), len(self._dst), 0)
+            r = L.ZSTD_compressStream2(self._z, C.byref(ob), C.byref(ib), end_op)
+            if N.is_error(r):
+                raise ZstdException(N.error_code(r), L.ZSTD_getErrorName(r).decode())
+            if ob.pos:
+                self._out.write(bytes(self._dst[: ob.pos]))
+            if end_op == ZSTD_e_continue:
+                if ib.pos == ib.size and ob.pos < ob.size:
+                    break
+            elif r == 0:
+                break
+
+    def write(self, data):
+        if self._closed:
+            raise IOError("StreamClosed")
+        self._step(bytes(data), ZSTD_e_continue)
+
+    def flush(self):
+        if self._closed:
+            raise IOError("StreamClosed")
+        self._step(b"", ZSTD_e_flush)
+        if hasattr(self._out, "flush"):
+            self._out.flush()
+
+    def close(self):
+        if self._closed:
+            return
+        self._step(b"", ZSTD_e_end)
+        N.lib().ZSTD_freeCStream(self._z)
+        self._closed = True
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class ZstdInputStream:
+    """J/ZstdInputStreamNoFinalizer.java:148-226 over ZSTD_decompressStream."""
+
+    def __init__(self, inp):
+        self._in = inp
+        L = N.lib()
+        self._z = L.ZSTD_createDStream()
+        L.ZSTD_initDStream(self._z)
+        self._src = b""
+        self._pos = 0
+        self._eof = False
+        self._closed = False
+
+    def read(self, n: int = -1) -> bytes:
+        if self._closed:
+            raise IOError("Stream closed")
+        L = N.lib()
+        chunks = []
+        want = n if n >= 0 else 1 << 62
+        dst = bytearray(L.ZSTD_DStreamOutSize())
+        d = (C.c_char * len(dst)).from_buffer(dst)
+        while want > 0:
+            if self._pos == len(self._src) and not self._eof:
+                self._src = self._in.read(L.ZSTD_DStreamInSize())
+                self._pos = 0
+                if not self._src:
+                    self._eof = True
+            src = np.frombuffer(self._src, dtype=np.uint8) if self._src else np.empty(0, dtype=np.uint8)
+            ib = N.InBuffer(src.ctypes.data if src.size else 0, src.size, self._pos)
+            ob = N.OutBuffer(C.addressof(d), min(len(dst), want), 0)
+            r = L.ZSTD_decompressStream(self._z, C.byref(ob), C.byref(ib))
+            if N.is_error(r):
+                raise ZstdException(N.error_code(r), L.ZSTD_getErrorName(r).decode())
+            self._pos = ib.pos
+            if ob.pos:
+                chunks.append(bytes(dst[: ob.pos]))
+                want -= ob.pos
+            elif self._eof and self._pos == len(self._src):
+                if r != 0:
+                    raise IOError("Truncated source")    # J/ZstdInputStreamNoFinalizer.java:187-197
+                break
+        return b"".join(chunks)
+
+    def close(self):
+        if not self._closed:
+            N.lib().ZSTD_freeDStream(self._z)
+            self._closed = True
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
