@@ -41,20 +41,23 @@ d_out = torch.empty(n * stride, dtype=torch.uint8, device=dev)
 d_ooff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
 d_back = torch.empty(n * 131072, dtype=torch.uint8, device=dev)
 d_res = torch.zeros(n, dtype=torch.int64, device=dev)
-st = torch.cuda.current_stream().cuda_stream
+stream = torch.cuda.Stream()
+st = stream.cuda_stream
 def comp():
     L.zstdb200_compress_device(ctx.handle, 3, n, d_src.data_ptr(), d_off.data_ptr(), d_slots.data_ptr(), stride, d_sizes.data_ptr(), st)
     L.zstdb200_compact_device(ctx.handle, n, d_slots.data_ptr(), stride, d_sizes.data_ptr(), d_out.data_ptr(), d_ooff.data_ptr(), st)
 def decomp():
     L.zstdb200_decompress_device(ctx.handle, n, d_out.data_ptr(), d_ooff.data_ptr(), d_back.data_ptr(), d_off.data_ptr(), d_res.data_ptr(), st)
-for name, opt, vals in (("enc", "enc_warps_per_sm", [0, 8, 4, 2, 1]), ("dec", "dec_warps_per_sm", [0, 8, 4])):
+for name, opt, vals in (("enc", "enc_warps_per_sm", [0, 12, 8, 4, 2, 1]), ("dec", "dec_warps_per_sm", [0, 8, 4, 2])):
     for v in vals:
         ctx.setOption(opt, v)
         fn = comp if name == "enc" else decomp
         if name == "dec": ctx.setOption("enc_warps_per_sm", 0); comp()
-        fn(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         print(f"{name} warps/SM={v}: {ms:.2f} ms  -> {n*131072/ms/1e6:.2f} GB/s uncompressed")
 torch.cuda.synchronize()

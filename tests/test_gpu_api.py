@@ -1,0 +1,127 @@
+"""The Python mirror of the Java API, on the GPU (-m gpu).  Modelled on the reference's own tests,
+src/test/scala/Zstd.scala: round trips over sizes straddling a block (:20-111), dst-too-small errors
+(:186-221), use-after-close (:1000-1020), Input/Output streams (:223-297, :426-488)."""
+import io
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs():
+    rng = np.random.default_rng(3)
+    from zstd_jni_b200 import corpus
+    out = [b"", b"a", rng.integers(0, 256, 1000, dtype=np.uint8).tobytes(), corpus.chunk(0)[:70000].tobytes(), corpus.chunk(5).tobytes(),
+           rng.integers(0, 256, 131072, dtype=np.uint8).tobytes(), corpus.chunk(2)[:130 * 1024].tobytes()]
+    return out
+
+
+@pytest.mark.parametrize("level", [1, 3])
+def test_zstd_compress_decompress_roundtrip(level):        # Zstd.scala:26-36
+    from zstd_jni_b200.zstd import Zstd
+    from tests.oracle_util import oracle_compress
+    for data in _inputs():
+        z = Zstd.compress(data, level)
+        assert z == oracle_compress(data, level)
+        assert Zstd.getFrameContentSize(z) == len(data)
+        assert Zstd.decompress(z, len(data)) == data
+
+
+def test_manual_buffers_and_too_small_dst():                # Zstd.scala:38-53,186-221
+    from zstd_jni_b200.zstd import Zstd, ZstdCompressCtx, ZstdDecompressCtx, ZstdException
+    data = _inputs()[3]
+    dst = bytearray(Zstd.compressBound(len(data)))
+    n = Zstd.compressInto(dst, data, 3)
+    assert not Zstd.isError(n)
+    out = bytearray(len(data))
+    assert Zstd.decompressInto(out, bytes(dst[:n])) == len(data) and bytes(out) == data
+    small = bytearray(len(data) - 1)
+    r = Zstd.decompressInto(small, bytes(dst[:n]))
+    assert Zstd.isError(r) and Zstd.getErrorCode(r) == 70
+    tiny = bytearray(10)
+    r = Zstd.compressInto(tiny, data, 3)
+    assert Zstd.isError(r) and Zstd.getErrorCode(r) == 70
+    with ZstdDecompressCtx() as d, pytest.raises(ZstdException) as ei:
+        d.decompress(bytes(dst[:n]), len(data) - 1)
+    assert ei.value.getErrorCode() == 70
+    with ZstdCompressCtx() as c:
+        c.setLevel(3)
+        buf = bytearray(200000)
+        k = c.compressByteArray(buf, 100, 150000, b"junk" + data + b"junk", 4, len(data))     # offsets honoured (jni_fast_zstd.c:615-639)
+        assert bytes(buf[100:100 + k]) == bytes(dst[:n])
+        with pytest.raises(IndexError):
+            c.compressByteArray(buf, 100, 10 ** 6, data, 0, len(data))
+
+
+def test_unsupported_parameters_are_reported():
+    from zstd_jni_b200.zstd import ZstdCompressCtx, ZstdException
+    data = _inputs()[3]
+    with ZstdCompressCtx() as c:
+        c.setLevel(3).setChecksum(True)
+        with pytest.raises(ZstdException) as ei:
+            c.compress(data)
+        assert ei.value.getErrorCode() == 40
+    with ZstdCompressCtx() as c:
+        c.setLevel(19)
+        with pytest.raises(ZstdException) as ei:
+            c.compress(data)
+        assert ei.value.getErrorCode() == 40
+    with ZstdCompressCtx() as c:                             # > one block: outside the bit-exact scope => refused, not approximated
+        with pytest.raises(ZstdException):
+            c.compress(bytes(200000))
+
+
+def test_use_after_close():                                  # Zstd.scala:1000-1020,1072-1080
+    from zstd_jni_b200.zstd import ZstdCompressCtx, ZstdDecompressCtx
+    c = ZstdCompressCtx(); c.close(); c.close()
+    with pytest.raises(RuntimeError, match="Closed"):
+        c.compress(b"abc")
+    d = ZstdDecompressCtx(); d.close()
+    with pytest.raises(RuntimeError, match="Closed"):
+        d.decompress(b"abc", 3)
+
+
+def test_output_and_input_streams():                         # Zstd.scala:223-297
+    from zstd_jni_b200.zstd import ZstdInputStream, ZstdOutputStream
+    from tests.oracle_util import oracle_decompress
+    from zstd_jni_b200 import corpus
+    data = b"".join(corpus.chunk(i).tobytes() for i in (0, 1, 2))[:300001]
+    sink = io.BytesIO()
+    with ZstdOutputStream(sink, 3) as zo:
+        for k in range(0, len(data), 50000):
+            zo.write(data[k:k + 50000])
+        zo.flush()
+    z = sink.getvalue()
+    assert oracle_decompress(z, len(data)) == data           # any zstd decoder reads the independent-frames stream
+    with ZstdInputStream(io.BytesIO(z)) as zi:
+        got = b""
+        while True:
+            part = zi.read(70000)
+            if not part:
+                break
+            got += part
+    assert got == data
+    # 1 byte at a time upstream (Zstd.scala:447-467)
+    class OneByte(io.RawIOBase):
+        def __init__(self, b): self.b = b; self.p = 0
+        def read(self, n=-1):
+            if self.p >= len(self.b): return b""
+            self.p += 1; return self.b[self.p - 1:self.p]
+    small = data[:40000]
+    sink = io.BytesIO()
+    with ZstdOutputStream(sink, 1) as zo:
+        zo.write(small)
+    with ZstdInputStream(OneByte(sink.getvalue())) as zi:
+        assert zi.read() == small
+    # empty stream
+    sink = io.BytesIO()
+    ZstdOutputStream(sink, 3).close()
+    assert oracle_decompress(sink.getvalue(), 0) == b""
+
+
+def test_input_stream_reads_reference_golden(reference_resources):   # Zstd.scala:426-446
+    from zstd_jni_b200.zstd import ZstdInputStream
+    xml = (reference_resources / "xml").read_bytes()
+    with ZstdInputStream(open(reference_resources / "xml-3.zst", "rb")) as zi:
+        assert zi.read() == xml

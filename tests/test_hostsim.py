@@ -1,0 +1,64 @@
+"""CPU tests of the *kernel source itself*: zstd_jni_b200/csrc/*.cuh instantiated with a 1-lane warp
+context (tests/hostsim/zb_hostsim.cpp) must agree with the oracle byte for byte.  This is how format
+logic is iterated on without a GPU; the CUDA build of the same source is checked by the -m gpu tests."""
+import hashlib
+import json
+from pathlib import Path
+
+import pytest
+
+from tests import cases
+from tests.oracle_util import hostsim_compress, hostsim_decompress, oracle_compress, oracle_decompress, ref, ref_stream_compress
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+@pytest.mark.parametrize("level", [3, 1, 4, 2, -1, -7])
+def test_hostsim_encoder_matches_oracle(level):
+    for name, data in cases.special_cases() + cases.corpus_cases(16) + cases.edge_cases(classes=(0, 2, 4, 5, 7)):
+        exp = oracle_compress(data, level)
+        got = hostsim_compress(data, level)
+        assert got == exp, (name, level, exp if isinstance(exp, int) else len(exp), got if isinstance(got, int) else len(got))
+
+
+def test_hostsim_decoder_on_golden_fixtures():
+    man = json.loads((GOLDEN / "manifest.json").read_text())
+    from tests.golden.make_golden import regenerate_input
+    for e in man["oneshot"]:
+        data = regenerate_input(e["input"])
+        assert hostsim_decompress((GOLDEN / e["file"]).read_bytes(), len(data)) == data, e["file"]
+    for e in man["decode_only"]:
+        out = hostsim_decompress((GOLDEN / e["file"]).read_bytes(), e["size"])
+        assert not isinstance(out, int) and hashlib.sha256(out).hexdigest() == e["sha256"], e["file"]
+    for e in man["errors"]:
+        assert hostsim_decompress((GOLDEN / e["file"]).read_bytes(), e["cap"]) == -e["code"], e["file"]
+
+
+def test_hostsim_decoder_reference_goldens(reference_resources):
+    xml = (reference_resources / "xml").read_bytes()
+    for name in ["xml-1.zst", "xml-3.zst", "xml-6.zst", "xml-9.zst", "xml-1-sized.zst", "xml-advanced.zst"]:
+        assert hostsim_decompress((reference_resources / name).read_bytes(), len(xml)) == xml, name
+
+
+def test_hostsim_decoder_matches_oracle_on_corruptions():
+    import numpy as np
+    from zstd_jni_b200 import corpus
+    rng = np.random.default_rng(11)
+    for idx in (0, 1, 2, 4, 5):
+        data = corpus.chunk(idx)[:40000].tobytes()
+        z = bytearray(oracle_compress(data, 3))
+        for _ in range(40):
+            zz = bytearray(z)
+            k = int(rng.integers(0, len(zz)))
+            zz[k] ^= 1 << int(rng.integers(0, 8))
+            a = oracle_decompress(bytes(zz), len(data)); b = hostsim_decompress(bytes(zz), len(data))
+            assert a == b, (idx, k, a if isinstance(a, int) else "ok", b if isinstance(b, int) else "ok")
+
+
+@pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
+def test_hostsim_decodes_reference_streams():
+    from zstd_jni_b200 import corpus
+    data = b"".join(corpus.chunk(i).tobytes() for i in (3, 2, 4))[:300000]
+    for level in (3, 9):
+        z = ref_stream_compress(data, level, checksum=True)
+        assert hostsim_decompress(z, len(data)) == data
