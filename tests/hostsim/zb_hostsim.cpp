@@ -6,6 +6,7 @@
 #include <cstring>
 #include "../../zstd_jni_b200/csrc/zb_decode.cuh"
 #include "../../zstd_jni_b200/csrc/zb_encode.cuh"
+#include "simt_emu.h"
 
 extern "C" {
 
@@ -38,6 +39,42 @@ size_t zbh_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     memcpy(in + 16, src, srcSize);
     u8* out = (u8*)calloc(1, dstCapacity + 64);
     size_t const r = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch);
+    if (!isErr(r)) memcpy(dst, out + 16, r);
+    free(S); free(scratch); free(in); free(out);
+    return r;
+}
+
+// ---- the same entry points on an emulated 32-lane warp (simt_emu.h): exercises the cooperative code paths
+size_t zbe_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level) {
+    using namespace zb;
+    if (srcSize > BLOCKSIZE_MAX) return ERR(E_srcSize_wrong);
+    EncShared* S = (EncShared*)calloc(1, sizeof(EncShared));
+    u8* wk = (u8*)calloc(1, enc_work_bytes() + 64);
+    EncWork W = enc_work_carve(wk);
+    size_t const bound = compress_bound(srcSize);
+    u8* slot = (u8*)calloc(1, bound + 64);
+    u8* in = (u8*)calloc(1, srcSize + 64);
+    memcpy(in + 16, src, srcSize);
+    size_t results[32];
+    run_warp([&](const WarpEmu& w) { results[w.lane] = compress_frame(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level); });
+    size_t r = results[0];
+    for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);   // the return value must be warp-uniform
+    if (!isErr(r)) { if (r > dstCapacity) r = ERR(E_dstSize_tooSmall); else memcpy(dst, slot, r); }
+    free(S); free(wk); free(slot); free(in);
+    return r;
+}
+
+size_t zbe_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize) {
+    using namespace zb;
+    DecShared* S = (DecShared*)calloc(1, sizeof(DecShared));
+    u8* scratch = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
+    u8* in = (u8*)calloc(1, srcSize + 64);
+    memcpy(in + 16, src, srcSize);
+    u8* out = (u8*)calloc(1, dstCapacity + 64);
+    size_t results[32];
+    run_warp([&](const WarpEmu& w) { results[w.lane] = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch); });
+    size_t r = results[0];
+    for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);
     if (!isErr(r)) memcpy(dst, out + 16, r);
     free(S); free(scratch); free(in); free(out);
     return r;

@@ -64,6 +64,20 @@ ZB_HD u32 ctz64(u64 v) {
     return (u32)__builtin_ctzll(v);
 #endif
 }
+ZB_HD u32 popc32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return (u32)__popc(v);
+#else
+    return (u32)__builtin_popcount(v);
+#endif
+}
+ZB_HD u32 ctz32(u32 v) {   // v != 0
+#if defined(__CUDA_ARCH__)
+    return (u32)__ffs((int)v) - 1u;
+#else
+    return (u32)__builtin_ctz(v);
+#endif
+}
 ZB_HD u32 umin(u32 a, u32 b) { return a < b ? a : b; }
 ZB_HD u32 umax(u32 a, u32 b) { return a > b ? a : b; }
 
@@ -145,6 +159,8 @@ struct WarpDev {
     static constexpr int W = 32;
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     template <class T> __device__ __forceinline__ T bcast(T v, int src = 0) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
+    __device__ __forceinline__ u32 match_any(u32 v) const { return __match_any_sync(0xFFFFFFFFu, v); }
     __device__ __forceinline__ u32 ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
     __device__ __forceinline__ u32 sum(u32 v) const {
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -162,6 +178,8 @@ struct WarpHost {
     static constexpr int W = 1;
     void sync() const {}
     template <class T> T bcast(T v, int = 0) const { return v; }
+    template <class T> T shfl(T v, int) const { return v; }
+    u32 match_any(u32) const { return 1u; }
     u32 ballot(bool p) const { return p ? 1u : 0u; }
     u32 sum(u32 v) const { return v; }
     u32 max(u32 v) const { return v; }

@@ -204,6 +204,198 @@ ZB_HDN u32 parse_dfast(const EncWork& W, const u8* src, size_t srcSize, u32 hBit
     return nbSeq;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative dfast parser (W = 32).  Produces exactly the sequences of parse_dfast() above.
+//
+// The greedy parse is a chain of decisions, but between two matches the reference just walks
+// positions ip, ip+step, ... doing, per position: hash, two table reads, two table writes and up to
+// three candidate compares.  A batch of consecutive positions is evaluated by consecutive lanes at
+// once.  What lane j must observe is the table as left by positions < j: lanes forward their own
+// pending writes to later lanes with __match_any_sync (same slot => the closest earlier lane wins),
+// the first lane that finds a match ends the batch, and only lanes up to it commit their writes
+// (last writer per slot).  Match extension and the backward catch-up are ballots over 8-byte /
+// 1-byte compares.  The batch width adapts (4 -> 32) so that match-dense data does not pay for 32
+// speculative probes per sequence.
+ZB_HD u32 hash8v(u64 d, u32 hBits) { return (u32)((d * 0xCF1BBCDCB7A56463ULL) >> (64 - hBits)); }
+ZB_HD u32 hashSv(u64 d, u32 hBits, u32 mls) {
+    switch (mls) {
+    default:
+    case 4: return ((u32)d * 2654435761U) >> (32 - hBits);
+    case 5: return (u32)(((d << 24) * 889523592379ULL) >> (64 - hBits));
+    case 6: return (u32)(((d << 16) * 227718039650203ULL) >> (64 - hBits));
+    case 7: return (u32)(((d << 8) * 58295818150454627ULL) >> (64 - hBits));
+    }
+}
+// common prefix length of src[a..n) and src[b..) (b < a), all lanes cooperate; uniform result
+template <class C>
+ZB_HD u32 wcount(const C& w, const u8* src, u32 n, u32 a, u32 b) {
+    u32 total = 0;
+    u32 lanes = 8;                       // most matches are short: start with 64 bytes, then full width
+    for (;;) {
+        u32 const pa = a + total + 8u * (u32)w.lane;
+        bool const on = (u32)w.lane < lanes;
+        u32 const avail = (on && pa < n) ? (n - pa < 8 ? n - pa : 8) : 0;
+        u32 cnt = 0;
+        if (avail) {
+            u64 const da = load64_n(src + pa, avail), db = load64_n(src + (b + total + 8u * (u32)w.lane), avail);
+            u64 diff = da ^ db;
+            if (avail < 8) diff &= (1ull << (avail * 8)) - 1;
+            cnt = diff ? (ctz64(diff) >> 3) : avail;
+        }
+        u32 const notFull = w.ballot(!on || cnt < 8) & ((lanes >= 32) ? 0xFFFFFFFFu : ((1u << lanes) - 1));
+        if (notFull) {
+            u32 const f = ctz32(notFull);
+            return total + 8 * f + w.shfl(cnt, (int)f);
+        }
+        total += 8 * lanes;
+        lanes = 32;
+    }
+}
+// backward extension: how many bytes before (ip, m) are equal, limited by maxBack; uniform result
+template <class C>
+ZB_HD u32 wcatchup(const C& w, const u8* src, u32 ip, u32 m, u32 maxBack) {
+    u32 total = 0;
+    for (;;) {
+        u32 const k = total + (u32)w.lane;
+        bool const eq = (k < maxBack) && (src[ip - 1 - k] == src[m - 1 - k]);
+        u32 const mask = w.ballot(eq);
+        if (mask != 0xFFFFFFFFu) return total + ctz32(~mask);
+        total += 32;
+    }
+}
+
+template <class C>
+ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t srcSize, u32 hBitsL, u32 hBitsS, u32 mls, u32* lastLL) {
+    u32* const hashLong = W.hashLong; u32* const hashSmall = W.hashSmall;
+    int const n = (int)srcSize, ilimit = n - 8;
+    int ip = 1, anchor = 0;
+    u32 off1 = 1, off2 = 0;             // {1,4,8} clipped by maxRep = 1 at position 1 (zstd_double_fast.c:158-164)
+    u32 nbSeq = 0;
+    u32 const lane = (u32)w.lane;
+    for (;;) {   // one iteration per stored match
+        u32 step = 1; int nextStep = ip + 256, ip1 = ip + 1;
+        if (ip1 > ilimit) break;
+        u32 width = 4;
+        int ev = -1;                      // event lane
+        // values of the batch that found the event (per lane)
+        int p = 0, p1 = 0; u32 st = 1; int ns = 0; u64 d8 = 0; u32 hl = 0, idxl = 0, idxs = 0, kind = 0, nActive = 0;
+        for (;;) {   // batches of `width` consecutive search positions
+            p = ip; p1 = ip1; st = step; ns = nextStep;
+            if (step == 1 && ip + (int)width + 1 < nextStep) { p = ip + (int)lane; p1 = p + 1; }
+            else for (u32 j = 0; j < lane && j < width; j++) { if (p1 >= ns) { st++; ns += 256; } p = p1; p1 += (int)st; }
+            bool const active = lane < width && p1 <= ilimit;
+            d8 = active ? load64(src + p) : 0;
+            hl = hash8v(d8, hBitsL);
+            u32 const hs = hashSv(d8, hBitsS, mls);
+            u32 const tl = active ? hashLong[hl] : 0, ts = active ? hashSmall[hs] : 0;
+            u32 const mL = w.match_any(active ? hl : (0x80000000u | lane));
+            u32 const mS = w.match_any(active ? hs : (0x80000000u | lane));
+            u32 const below = (1u << lane) - 1;
+            u32 const lowL = mL & below, lowS = mS & below;
+            int const pL = w.shfl(p, lowL ? (int)highbit32(lowL) : (int)lane);
+            int const pS = w.shfl(p, lowS ? (int)highbit32(lowS) : (int)lane);
+            idxl = lowL ? (u32)pL + 2 : tl;
+            idxs = lowS ? (u32)pS + 2 : ts;
+            kind = 0;
+            if (active) {
+                bool const repOk = (off1 > 0) && (load32(src + p + 1 - (int)off1) == (u32)(d8 >> 8));
+                bool const longOk = (idxl >= 2) && (load64(src + (idxl - 2)) == d8);
+                bool const shortOk = (idxs >= 2) && (load32(src + (idxs - 2)) == (u32)d8);
+                kind = repOk ? 1 : longOk ? 2 : shortOk ? 3 : 0;
+            }
+            u32 const hm = w.ballot(kind != 0);
+            nActive = popc32(w.ballot(active));
+            ev = hm ? (int)ctz32(hm) : -1;
+            int const last = ev >= 0 ? ev : (int)nActive - 1;
+            if (active && (int)lane <= last) {
+                u32 const later = ((last >= 31) ? 0xFFFFFFFFu : ((2u << last) - 1)) & ~((2u << lane) - 1);
+                if (!(mL & later)) hashLong[hl] = (u32)p + 2;
+                if (!(mS & later)) hashSmall[hs] = (u32)p + 2;
+            }
+            w.sync();
+            if (ev >= 0) break;
+            // no match in this batch: continue after its last position
+            {   int const L = (int)nActive - 1;
+                int np = p, np1 = p1; u32 nst = st; int nns = ns;
+                if (np1 >= nns) { nst++; nns += 256; }
+                np = np1; np1 += (int)nst;
+                ip = w.shfl(np, L); ip1 = w.shfl(np1, L); step = w.shfl(nst, L); nextStep = w.shfl(nns, L); }
+            if (ip1 > ilimit) break;
+            width = width < 32 ? width * 2 : 32;
+        }
+        if (ev < 0) break;
+        // ---- event at lane ev: gather what the serial code would hold at this point
+        int const pe = w.shfl(p, ev), p1e = w.shfl(p1, ev);
+        u32 const ste = w.shfl(st, ev), kinde = w.shfl(kind, ev), idxle = w.shfl(idxl, ev), idxse = w.shfl(idxs, ev);
+        bool const nextInBatch = (ev + 1 < (int)nActive);
+        int const nl = nextInBatch ? ev + 1 : ev;
+        u32 hl1 = w.shfl(hl, nl), idxl1 = w.shfl(idxl, nl); u64 d81 = w.shfl(d8, nl);
+        if (kinde != 1 && !nextInBatch) {   // position ip1 was not part of the batch: read it now (tables are committed)
+            d81 = load64(src + p1e); hl1 = hash8v(d81, hBitsL); idxl1 = hashLong[hl1];
+        }
+        u32 mLength, offset = 0; int mpos;
+        if (kinde == 1) {
+            ip = pe + 1;
+            mLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)ip + 4 - off1) + 4;
+            if (lane == 0) { W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = mLength; }
+            nbSeq++;
+        } else {
+            ip = pe;
+            if (kinde == 2) {
+                mpos = (int)idxle - 2;
+                mLength = wcount(w, src, (u32)n, (u32)ip + 8, (u32)mpos + 8) + 8;
+                offset = (u32)(ip - mpos);
+            } else {
+                mpos = (int)idxse - 2;
+                mLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)mpos + 4) + 4;
+                offset = (u32)(ip - mpos);
+                if ((idxl1 > 2) && (load64(src + (idxl1 - 2)) == d81)) {
+                    int const m1 = (int)idxl1 - 2;
+                    u32 const l1len = wcount(w, src, (u32)n, (u32)p1e + 8, (u32)m1 + 8) + 8;
+                    if (l1len > mLength) { ip = p1e; mLength = l1len; offset = (u32)(ip - m1); mpos = m1; }
+                }
+            }
+            {   u32 const maxBack = (u32)(ip - anchor) < (u32)mpos ? (u32)(ip - anchor) : (u32)mpos;
+                u32 const back = maxBack ? wcatchup(w, src, (u32)ip, (u32)mpos, maxBack) : 0;
+                ip -= (int)back; mLength += back; }
+            off2 = off1; off1 = offset;
+            if (lane == 0) {
+                if (ste < 4) hashLong[hl1] = (u32)p1e + 2;
+                W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = offset + 3; W.seqML[nbSeq] = mLength;
+            }
+            nbSeq++;
+        }
+        ip += (int)mLength; anchor = ip;
+        if (ip <= ilimit) {
+            if (lane == 0) {   // complementary insertions, in the reference's order (:297-305)
+                u32 const A = (u32)pe + 2;
+                u64 const dA = load64(src + A), dB = load64(src + ip - 2), dC = load64(src + ip - 1);
+                hashLong[hash8v(dA, hBitsL)] = A + 2;
+                hashLong[hash8v(dB, hBitsL)] = (u32)ip - 2 + 2;
+                hashSmall[hashSv(dA, hBitsS, mls)] = A + 2;
+                hashSmall[hashSv(dC, hBitsS, mls)] = (u32)ip - 1 + 2;
+            }
+            w.sync();
+            while ((ip <= ilimit) && (off2 > 0) && (load32(src + ip) == load32(src + ip - (int)off2))) {   // :308-320
+                u32 const rLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)ip + 4 - off2) + 4;
+                u32 const t = off2; off2 = off1; off1 = t;
+                if (lane == 0) {
+                    u64 const d = load64(src + ip);
+                    hashSmall[hashSv(d, hBitsS, mls)] = (u32)ip + 2;
+                    hashLong[hash8v(d, hBitsL)] = (u32)ip + 2;
+                    W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength;
+                }
+                nbSeq++;
+                ip += (int)rLength; anchor = ip;
+                w.sync();
+            }
+        } else w.sync();
+    }
+    w.sync();
+    *lastLL = (u32)(n - anchor);
+    return nbSeq;
+}
+
 // ---- forward bit writer (LSB first); close appends the 1-bit end mark.
 // Mirrors BIT_CStream_t / HUF_CStream_t bounds: 8 bytes of slack are required (bitstream.h:226-242).
 struct BitW {
@@ -963,12 +1155,16 @@ ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst
             for (u32 i = (u32)w.lane; i < nS; i += C::W) W.hashSmall[i] = 0;
             w.sync(); }
         u32 nbSeq = 0, lastLL = 0;
-        if (w.lane == 0) {
-            if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
-            else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
+        if (C::W > 1 && cp.strategy == S_dfast) {
+            nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
+        } else {
+            if (w.lane == 0) {
+                if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
+                else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
+            }
+            w.sync();
+            nbSeq = w.bcast(nbSeq); lastLL = w.bcast(lastLL);
         }
-        w.sync();
-        nbSeq = w.bcast(nbSeq); lastLL = w.bcast(lastLL);
         // gather literals (ZSTD_storeSeq copies them during the parse; the result is the same buffer)
         size_t litSize = 0;
         {   size_t sp = 0;
