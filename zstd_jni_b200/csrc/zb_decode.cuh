@@ -404,7 +404,7 @@ ZB_HDN size_t decode_block(const C& w, DecShared& S, const u8* frameStart, u8* o
         w.sync();
     }
 
-    u8* op = op0; u8* const oend = op0 + (cap < blockSizeMax ? cap : blockSizeMax);
+    u8* op = op0; u8* const oend = op0 + cap;   // like the reference, a block is bounded by the destination only
     const u8* const litEnd = lit + litSize;
     size_t err = 0;
     if (nbSeq) {
