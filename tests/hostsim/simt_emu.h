@@ -24,9 +24,11 @@ struct WarpEmuShared {
     int current = 0;
 };
 
-struct WarpEmu {
+template <int LANES>
+struct WarpEmuT {
     int lane = 0;
-    static constexpr int W = 32;
+    static constexpr int W = LANES;
+    static constexpr uint32_t FULL = (LANES >= 32) ? 0xFFFFFFFFu : ((1u << (LANES & 31)) - 1);
     WarpEmuShared* sh = nullptr;
     mutable uint64_t uses[2] = {0, 0};
     mutable unsigned seq = 0;
@@ -38,41 +40,43 @@ struct WarpEmu {
         sh->slot[b][lane] = v;
         sh->arrived[b]++;
         uses[b]++;
-        while (sh->arrived[b] < 32 * uses[b]) yield();
+        while (sh->arrived[b] < (uint64_t)LANES * uses[b]) yield();
         return sh->slot[b];
     }
     void sync() const { (void)exchange(0); }
     template <class T> T shfl(T v, int src) const {
         uint64_t raw = 0; static_assert(sizeof(T) <= 8, "shfl payload"); memcpy(&raw, &v, sizeof(T));
         const uint64_t* all = exchange(raw);
-        T out; memcpy(&out, &all[src & 31], sizeof(T)); return out;
+        T out; memcpy(&out, &all[src & (LANES - 1)], sizeof(T)); return out;
     }
     template <class T> T bcast(T v, int src = 0) const { return shfl(v, src); }
-    uint32_t ballot(bool p) const { const uint64_t* all = exchange(p ? 1 : 0); uint32_t m = 0; for (int i = 0; i < 32; i++) m |= (uint32_t)(all[i] & 1) << i; return m; }
-    uint32_t sum(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t s = 0; for (int i = 0; i < 32; i++) s += (uint32_t)all[i]; return s; }
-    uint32_t max(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t s = 0; for (int i = 0; i < 32; i++) if ((uint32_t)all[i] > s) s = (uint32_t)all[i]; return s; }
-    uint32_t match_any(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t m = 0; for (int i = 0; i < 32; i++) if ((uint32_t)all[i] == v) m |= 1u << i; return m; }
+    uint32_t ballot(bool p) const { const uint64_t* all = exchange(p ? 1 : 0); uint32_t m = 0; for (int i = 0; i < LANES; i++) m |= (uint32_t)(all[i] & 1) << i; return m; }
+    uint32_t sum(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t s = 0; for (int i = 0; i < LANES; i++) s += (uint32_t)all[i]; return s; }
+    uint32_t max(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t s = 0; for (int i = 0; i < LANES; i++) if ((uint32_t)all[i] > s) s = (uint32_t)all[i]; return s; }
+    uint32_t match_any(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t m = 0; for (int i = 0; i < LANES; i++) if ((uint32_t)all[i] == v) m |= 1u << i; return m; }
     void atomic_inc(uint32_t* p) const { ++*p; }
 };
 
+typedef WarpEmuT<32> WarpEmu;
 namespace emu_detail {
-struct Launch { std::function<void(const WarpEmu&)>* body; WarpEmuShared* sh; int lane; };
-inline void trampoline(unsigned lo, unsigned hi) {
-    Launch* l = reinterpret_cast<Launch*>(((uintptr_t)hi << 32) | lo);
-    WarpEmu w; w.lane = l->lane; w.sh = l->sh;
+template <int LANES> struct Launch { std::function<void(const WarpEmuT<LANES>&)>* body; WarpEmuShared* sh; int lane; };
+template <int LANES> inline void trampoline(unsigned lo, unsigned hi) {
+    Launch<LANES>* l = reinterpret_cast<Launch<LANES>*>(((uintptr_t)hi << 32) | lo);
+    WarpEmuT<LANES> w; w.lane = l->lane; w.sh = l->sh;
     (*l->body)(w);
     l->sh->done[l->lane] = true;
     swapcontext(&l->sh->lane_ctx[l->lane], &l->sh->main_ctx);
 }
 }  // namespace emu_detail
 
-// run `body` once per lane of an emulated warp
-inline void run_warp(std::function<void(const WarpEmu&)> body) {
+// run `body` once per lane of an emulated group of LANES lanes
+template <int LANES = 32>
+inline void run_warp(std::function<void(const WarpEmuT<LANES>&)> body) {
     WarpEmuShared* sh = new WarpEmuShared();
     size_t const stackSize = 1 << 20;
-    std::vector<void*> stacks(32);
-    std::vector<emu_detail::Launch> launches(32);
-    for (int i = 0; i < 32; i++) {
+    std::vector<void*> stacks(LANES);
+    std::vector<emu_detail::Launch<LANES>> launches(LANES);
+    for (int i = 0; i < LANES; i++) {
         sh->done[i] = false;
         stacks[i] = malloc(stackSize);
         getcontext(&sh->lane_ctx[i]);
@@ -81,11 +85,11 @@ inline void run_warp(std::function<void(const WarpEmu&)> body) {
         sh->lane_ctx[i].uc_link = &sh->main_ctx;
         launches[i] = {&body, sh, i};
         uintptr_t const p = reinterpret_cast<uintptr_t>(&launches[i]);
-        makecontext(&sh->lane_ctx[i], (void (*)())emu_detail::trampoline, 2, (unsigned)(p & 0xFFFFFFFFu), (unsigned)(p >> 32));
+        makecontext(&sh->lane_ctx[i], (void (*)())emu_detail::trampoline<LANES>, 2, (unsigned)(p & 0xFFFFFFFFu), (unsigned)(p >> 32));
     }
     for (;;) {
         bool any = false;
-        for (int i = 0; i < 32; i++) {
+        for (int i = 0; i < LANES; i++) {
             if (sh->done[i]) continue;
             any = true;
             sh->current = i;

@@ -55,10 +55,16 @@ size_t zbe_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSi
     u8* slot = (u8*)calloc(1, bound + 64);
     u8* in = (u8*)calloc(1, srcSize + 64);
     memcpy(in + 16, src, srcSize);
-    size_t results[32];
-    run_warp([&](const WarpEmu& w) { results[w.lane] = compress_frame(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level); });
+    // stage 1 on an 8-lane group (k_parse), stage 2 on a 32-lane warp (k_entropy), like the CUDA build
+    size_t results[32]; u32 nbSeqs[8], lastLLs[8];
+    run_warp<8>([&](const WarpEmuT<8>& w) { results[w.lane] = parse_stage(w, W, in + 16, srcSize, level, &nbSeqs[w.lane], &lastLLs[w.lane]); });
     size_t r = results[0];
-    for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);   // the return value must be warp-uniform
+    for (int i = 1; i < 8; i++) if (results[i] != r || nbSeqs[i] != nbSeqs[0] || lastLLs[i] != lastLLs[0]) r = ERR(E_GENERIC);
+    if (!isErr(r)) {
+        run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = encode_stage(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level, nbSeqs[0], lastLLs[0]); });
+        r = results[0];
+        for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);   // the return value must be warp-uniform
+    }
     if (!isErr(r)) { if (r > dstCapacity) r = ERR(E_dstSize_tooSmall); else memcpy(dst, slot, r); }
     free(S); free(wk); free(slot); free(in);
     return r;
@@ -72,7 +78,7 @@ size_t zbe_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     memcpy(in + 16, src, srcSize);
     u8* out = (u8*)calloc(1, dstCapacity + 64);
     size_t results[32];
-    run_warp([&](const WarpEmu& w) { results[w.lane] = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch); });
+    run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch); });
     size_t r = results[0];
     for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);
     if (!isErr(r)) memcpy(dst, out + 16, r);

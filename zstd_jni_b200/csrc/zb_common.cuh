@@ -154,28 +154,40 @@ static const CodeTables h_tables = ZB_CODE_TABLES_INIT;
 
 // ---- warp contexts
 #if defined(__CUDACC__)
-struct WarpDev {
-    int lane;
-    static constexpr int W = 32;
-    __device__ __forceinline__ void sync() const { __syncwarp(); }
-    template <class T> __device__ __forceinline__ T bcast(T v, int src = 0) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
-    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
-    __device__ __forceinline__ u32 match_any(u32 v) const { return __match_any_sync(0xFFFFFFFFu, v); }
-    __device__ __forceinline__ u32 ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
+// LANES consecutive lanes of a hardware warp acting as one cooperative group (LANES = 32: the whole warp).
+// Collectives name only the group's lanes, so several groups of one warp may diverge freely (sm_70+).
+template <int LANES>
+struct GroupDev {
+    int lane;        // lane inside the group
+    u32 gmask;       // the group's lanes inside the hardware warp
+    int gshift;      // first lane of the group
+    static constexpr int W = LANES;
+    static constexpr u32 FULL = (LANES >= 32) ? 0xFFFFFFFFu : ((1u << (LANES & 31)) - 1);
+    __device__ __forceinline__ static GroupDev make() {
+        int const l = (int)(threadIdx.x & 31), sh = l & ~(LANES - 1);
+        return GroupDev{l & (LANES - 1), (LANES >= 32) ? 0xFFFFFFFFu : (FULL << sh), sh};
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(gmask, v, src, LANES); }
+    template <class T> __device__ __forceinline__ T bcast(T v, int src = 0) const { return __shfl_sync(gmask, v, src, LANES); }
+    __device__ __forceinline__ u32 ballot(bool p) const { return (__ballot_sync(gmask, p) >> gshift) & FULL; }
+    __device__ __forceinline__ u32 match_any(u32 v) const { return (__match_any_sync(gmask, v) >> gshift) & FULL; }
     __device__ __forceinline__ u32 sum(u32 v) const {
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, LANES);
         return v;
     }
     __device__ __forceinline__ u32 max(u32 v) const {
-        for (int o = 16; o > 0; o >>= 1) { u32 t = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = t > v ? t : v; }
+        for (int o = LANES / 2; o > 0; o >>= 1) { u32 t = __shfl_xor_sync(gmask, v, o, LANES); v = t > v ? t : v; }
         return v;
     }
     __device__ __forceinline__ void atomic_inc(u32* p) const { atomicAdd(p, 1u); }
 };
+typedef GroupDev<32> WarpDev;
 #endif
 struct WarpHost {
     int lane = 0;
     static constexpr int W = 1;
+    static constexpr u32 FULL = 1u;
     void sync() const {}
     template <class T> T bcast(T v, int = 0) const { return v; }
     template <class T> T shfl(T v, int) const { return v; }

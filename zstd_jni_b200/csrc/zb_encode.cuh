@@ -230,7 +230,7 @@ ZB_HD u32 hashSv(u64 d, u32 hBits, u32 mls) {
 template <class C>
 ZB_HD u32 wcount(const C& w, const u8* src, u32 n, u32 a, u32 b) {
     u32 total = 0;
-    u32 lanes = 8;                       // most matches are short: start with 64 bytes, then full width
+    u32 lanes = C::W < 8 ? C::W : 8;     // most matches are short: start with 64 bytes, then full width
     for (;;) {
         u32 const pa = a + total + 8u * (u32)w.lane;
         bool const on = (u32)w.lane < lanes;
@@ -248,7 +248,7 @@ ZB_HD u32 wcount(const C& w, const u8* src, u32 n, u32 a, u32 b) {
             return total + 8 * f + w.shfl(cnt, (int)f);
         }
         total += 8 * lanes;
-        lanes = 32;
+        lanes = C::W;
     }
 }
 // backward extension: how many bytes before (ip, m) are equal, limited by maxBack; uniform result
@@ -259,8 +259,8 @@ ZB_HD u32 wcatchup(const C& w, const u8* src, u32 ip, u32 m, u32 maxBack) {
         u32 const k = total + (u32)w.lane;
         bool const eq = (k < maxBack) && (src[ip - 1 - k] == src[m - 1 - k]);
         u32 const mask = w.ballot(eq);
-        if (mask != 0xFFFFFFFFu) return total + ctz32(~mask);
-        total += 32;
+        if (mask != C::FULL) return total + ctz32(~mask);
+        total += C::W;
     }
 }
 
@@ -275,7 +275,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
     for (;;) {   // one iteration per stored match
         u32 step = 1; int nextStep = ip + 256, ip1 = ip + 1;
         if (ip1 > ilimit) break;
-        u32 width = 4;
+        u32 width = C::W < 4 ? C::W : 4;
         int ev = -1;                      // event lane
         // values of the batch that found the event (per lane)
         int p = 0, p1 = 0; u32 st = 1; int ns = 0; u64 d8 = 0; u32 hl = 0, idxl = 0, idxs = 0, kind = 0, nActive = 0;
@@ -321,7 +321,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
                 np = np1; np1 += (int)nst;
                 ip = w.shfl(np, L); ip1 = w.shfl(np1, L); step = w.shfl(nst, L); nextStep = w.shfl(nns, L); }
             if (ip1 > ilimit) break;
-            width = width < 32 ? width * 2 : 32;
+            width = width * 2 < (u32)C::W ? width * 2 : (u32)C::W;
         }
         if (ev < 0) break;
         // ---- event at lane ev: gather what the serial code would hold at this point
@@ -1122,10 +1122,44 @@ ZB_HDN u32 parse_fast(const EncWork& W, const u8* src, size_t srcSize, u32 hlog,
 }
 
 // ------------------------------------------------------------------ frame
-// One chunk -> one frame, as ZSTD_compress2 would emit it with dstCapacity = ZSTD_compressBound(srcSize).
+// A chunk becomes a frame in two stages that may run in different kernels (and with different group widths):
+//   parse_stage   match finding -> sequences (W.seq*), their count and the trailing literal run
+//   encode_stage  frame/block headers, literal gathering, Huffman + FSE entropy stage
+// Together they emit what ZSTD_compress2 would with dstCapacity = ZSTD_compressBound(srcSize).
+constexpr u32 PARSE_SKIPPED = 0xFFFFFFFFu;     // nbSeq marker: srcSize < 7, the block is stored raw (ZSTD_buildSeqStore :3273-3280)
+
+template <class C>
+ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t srcSize, int level, u32* nbSeqOut, u32* lastLLOut) {
+    CParams cp;
+    *nbSeqOut = PARSE_SKIPPED; *lastLLOut = 0;
+    if (!get_cparams(&cp, level, srcSize)) return ERR(E_parameter_unsupported);
+    if (srcSize < 7) return 0;
+    {   // fresh tables: zero the used part (16-byte stores; the workspace is 16-byte aligned)
+        u32 const nL = (1u << cp.hashLog) / 4, nS = (cp.strategy == S_dfast) ? (1u << cp.chainLog) / 4 : 0;
+        struct alignas(16) Q { u32 a, b, c, d; };
+        Q* const qL = reinterpret_cast<Q*>(W.hashLong); Q* const qS = reinterpret_cast<Q*>(W.hashSmall);
+        Q const z = { 0, 0, 0, 0 };
+        for (u32 i = (u32)w.lane; i < nL; i += C::W) qL[i] = z;
+        for (u32 i = (u32)w.lane; i < nS; i += C::W) qS[i] = z;
+        w.sync(); }
+    u32 nbSeq = 0, lastLL = 0;
+    if (C::W > 1 && cp.strategy == S_dfast) {
+        nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
+    } else {
+        if (w.lane == 0) {
+            if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
+            else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
+        }
+        w.sync();
+        nbSeq = w.bcast(nbSeq); lastLL = w.bcast(lastLL);
+    }
+    *nbSeqOut = nbSeq; *lastLLOut = lastLL;
+    return 0;
+}
+
 // `dst` must have room for compress_bound(srcSize) + 32 bytes.  Uniform return value.
 template <class C>
-ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level) {
+ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level, u32 nbSeq, u32 lastLL) {
     CParams cp;
     if (!get_cparams(&cp, level, srcSize)) return ERR(E_parameter_unsupported);
     if (dstCapacity < 18) return ERR(E_dstSize_tooSmall);
@@ -1148,23 +1182,7 @@ ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst
     u8* const op = dst + pos; size_t const cap = dstCapacity - pos;
     if (cap < 3 + 2 + 1) return ERR(E_dstSize_tooSmall);
     size_t cSize = 0;
-    if (srcSize >= 7) {   // ZSTD_buildSeqStore :3273-3280
-        // fresh tables: zero the used part
-        {   u32 const nL = 1u << cp.hashLog, nS = (cp.strategy == S_dfast) ? (1u << cp.chainLog) : 0;
-            for (u32 i = (u32)w.lane; i < nL; i += C::W) W.hashLong[i] = 0;
-            for (u32 i = (u32)w.lane; i < nS; i += C::W) W.hashSmall[i] = 0;
-            w.sync(); }
-        u32 nbSeq = 0, lastLL = 0;
-        if (C::W > 1 && cp.strategy == S_dfast) {
-            nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
-        } else {
-            if (w.lane == 0) {
-                if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
-                else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
-            }
-            w.sync();
-            nbSeq = w.bcast(nbSeq); lastLL = w.bcast(lastLL);
-        }
+    if (nbSeq != PARSE_SKIPPED) {
         // gather literals (ZSTD_storeSeq copies them during the parse; the result is the same buffer)
         size_t litSize = 0;
         {   size_t sp = 0;
@@ -1193,6 +1211,15 @@ ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst
     if (w.lane == 0) { u32 const h = 1 + (2 << 1) + (u32)(cSize << 3); op[0] = (u8)h; op[1] = (u8)(h >> 8); op[2] = (u8)(h >> 16); }
     w.sync();
     return pos + 3 + cSize;
+}
+
+// both stages on one context (host instantiation, single-kernel use)
+template <class C>
+ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level) {
+    u32 nbSeq = 0, lastLL = 0;
+    size_t const r = parse_stage(w, W, src, srcSize, level, &nbSeq, &lastLL);
+    if (isErr(r)) return r;
+    return encode_stage(w, S, W, dst, dstCapacity, src, srcSize, level, nbSeq, lastLL);
 }
 
 }  // namespace zb
