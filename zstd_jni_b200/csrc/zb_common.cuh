@@ -181,6 +181,17 @@ struct GroupDev {
         return v;
     }
     __device__ __forceinline__ void atomic_inc(u32* p) const { atomicAdd(p, 1u); }
+    // exclusive prefix sum over the group's lanes
+    __device__ __forceinline__ u32 exscan(u32 v) const {
+        u32 x = v;
+        for (int o = 1; o < LANES; o <<= 1) { u32 const t = __shfl_up_sync(gmask, x, o, LANES); if (lane >= o) x += t; }
+        return x - v;
+    }
+    // OR one byte into memory shared with neighbouring lanes (32-bit atomic on the containing word)
+    __device__ __forceinline__ void atomic_or_byte(u8* p, u32 v) const {
+        uintptr_t const a = reinterpret_cast<uintptr_t>(p);
+        atomicOr(reinterpret_cast<unsigned int*>(a & ~(uintptr_t)3), v << (8 * (u32)(a & 3)));
+    }
 };
 typedef GroupDev<32> WarpDev;
 #endif
@@ -196,6 +207,8 @@ struct WarpHost {
     u32 sum(u32 v) const { return v; }
     u32 max(u32 v) const { return v; }
     void atomic_inc(u32* p) const { ++*p; }
+    u32 exscan(u32) const { return 0; }
+    void atomic_or_byte(u8* p, u32 v) const { *p = (u8)(*p | v); }
 };
 
 }  // namespace zb

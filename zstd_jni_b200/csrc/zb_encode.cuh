@@ -63,9 +63,17 @@ struct EncWork {
     u32* seqML;
     u8* lit;            // BLOCKSIZE_MAX + 32
     u8* codes;          // 3 * MAX_SEQ
+    u16* stbits;        // 3 * MAX_SEQ : per sequence and stream, FSE state bits (value | nbBits << 12)
 };
+ZB_HD size_t enc_entropy_work_bytes() { return (size_t)(BLOCKSIZE_MAX + 32) + 3 * (size_t)MAX_SEQ + 64 + 6 * (size_t)MAX_SEQ + 64; }
+ZB_HD void enc_entropy_work_carve(EncWork& w, u8* base) {
+    w.lit = base; base += BLOCKSIZE_MAX + 32;
+    w.codes = base; base += 3 * (size_t)MAX_SEQ + 64;
+    base = reinterpret_cast<u8*>((reinterpret_cast<uintptr_t>(base) + 15) & ~(uintptr_t)15);
+    w.stbits = reinterpret_cast<u16*>(base);
+}
 ZB_HD size_t enc_work_bytes() {
-    return (size_t)2 * (4u << ENC_HASHLOG_MAX) + (size_t)3 * 4 * MAX_SEQ + (BLOCKSIZE_MAX + 32) + 3 * MAX_SEQ + 64;
+    return (size_t)2 * (4u << ENC_HASHLOG_MAX) + (size_t)3 * 4 * MAX_SEQ + enc_entropy_work_bytes() + 64;
 }
 ZB_HD EncWork enc_work_carve(u8* base) {
     EncWork w;
@@ -74,8 +82,7 @@ ZB_HD EncWork enc_work_carve(u8* base) {
     w.seqLL = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
     w.seqOF = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
     w.seqML = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
-    w.lit = base; base += BLOCKSIZE_MAX + 32;
-    w.codes = base;
+    enc_entropy_work_carve(w, base);
     return w;
 }
 
@@ -414,6 +421,27 @@ struct BitW {
         if (nb) { p[n] = (u8)acc; return n + 1; }
         return n;
     }
+};
+
+// ---- cooperative bit packing: every lane appends the bits of its own slice of a stream at a bit offset
+// obtained from a prefix sum over the slice sizes.  The region is zeroed first; bytes a lane fully owns are
+// plain stores, the (at most two) bytes it shares with its neighbours are OR-ed in atomically.
+template <class C>
+struct LaneBits {
+    u8* base; u32 bytePos; u64 acc; u32 nb; bool shared;
+    ZB_HD void init(u8* b, u32 startBit) { base = b; bytePos = startBit >> 3; nb = startBit & 7; acc = 0; shared = nb != 0; }
+    ZB_HD void emit(const C& w) {          // write all whole bytes held in acc
+        while (nb >= 8) {
+            if (shared) { w.atomic_or_byte(base + bytePos, (u32)(acc & 0xFF)); shared = false; }
+            else base[bytePos] = (u8)acc;
+            bytePos++; acc >>= 8; nb -= 8;
+        }
+    }
+    ZB_HD void add(const C& w, u32 v, u32 bits) {   // bits <= 31; v must fit in `bits`
+        acc |= (u64)v << nb; nb += bits;
+        if (nb >= 32) emit(w);
+    }
+    ZB_HD void close(const C& w) { emit(w); if (nb) w.atomic_or_byte(base + bytePos, (u32)(acc & 0xFF)); }
 };
 
 // ---- warp histogram of bytes; returns largest count, trims *maxSV (HIST_count_simple, hist.c:39-74)
@@ -792,12 +820,29 @@ ZB_HDN size_t huf_write_ctable(EncShared& S, u8* dst, size_t cap, u32 maxSV, u32
     for (u32 n = 0; n < maxSV; n += 2) dst[(n / 2) + 1] = (u8)((wt[n] << 4) + wt[n + 1]);
     return ((maxSV + 1) / 2) + 1;
 }
-// one Huffman stream (HUF_compress1X_usingCTable_internal_body :1055-1118): last symbol first, then end mark
-ZB_HDN size_t huf_encode_stream(const EncShared& S, u8* dst, size_t cap, const u8* src, size_t n) {
+// one Huffman stream (HUF_compress1X_usingCTable_internal_body :1055-1118): symbols are appended last-to-first
+// (LSB first), then a single 1 bit.  The whole group packs it: lane l takes the l-th slice of the emission
+// order, slice bit offsets come from an exclusive scan.  `totalBits` = sum of code lengths (without the mark).
+// Returns the stream size in bytes, 0 when it does not fit (same bounds as HUF_closeCStream :973-982).
+template <class C>
+ZB_HDN size_t huf_encode_stream(const C& w, const EncShared& S, u8* dst, size_t cap, const u8* src, size_t n, u32 totalBits) {
     if (cap <= 8) return 0;
-    BitW w; w.init(dst, cap);
-    for (size_t i = n; i > 0; i--) { u8 const b = src[i - 1]; w.add(S.hufCode[b], S.hufBits[b]); }
-    return w.close();
+    if ((((size_t)totalBits + 1) >> 3) >= cap - 8) return 0;
+    size_t const size = ((size_t)totalBits + 1 + 7) >> 3;
+    for (size_t i = (size_t)w.lane; i < size; i += C::W) dst[i] = 0;
+    w.sync();
+    u32 const B = (u32)((n + C::W - 1) / C::W);
+    u32 const j0 = (u32)w.lane * B < (u32)n ? (u32)w.lane * B : (u32)n;
+    u32 const j1 = j0 + B < (u32)n ? j0 + B : (u32)n;
+    u32 mine = 0;
+    for (u32 j = j0; j < j1; j++) mine += S.hufBits[src[n - 1 - j]];
+    u32 const start = w.exscan(mine);
+    LaneBits<C> lb; lb.init(dst, start);
+    for (u32 j = j0; j < j1; j++) { u8 const b = src[n - 1 - j]; lb.add(w, S.hufCode[b], S.hufBits[b]); }
+    if (w.lane == C::W - 1) lb.add(w, 1, 1);
+    lb.close(w);
+    w.sync();
+    return size;
 }
 
 // ZSTD_noCompressLiterals :39-66 / ZSTD_compressRleLiteralsBlock :81-107 ; warp copy
@@ -864,9 +909,10 @@ ZB_HDN size_t compress_literals(const C& w, EncShared& S, u8* dst, size_t cap, c
         u8* op = o + hSize; size_t const opcap = ocap - hSize;
         size_t total;
         if (single) {
-            size_t c = 0;
-            if (w.lane == 0) c = huf_encode_stream(S, op, opcap, src, n);
-            c = w.bcast(c);
+            u32 b = 0;
+            for (size_t i = (size_t)w.lane; i < n; i += C::W) b += S.hufBits[src[i]];
+            u32 const bits = w.sum(b);
+            size_t const c = huf_encode_stream(w, S, op, opcap, src, n, bits);
             if (c == 0) break;
             total = hSize + c;
         } else {
@@ -874,31 +920,24 @@ ZB_HDN size_t compress_literals(const C& w, EncShared& S, u8* dst, size_t cap, c
             if (opcap < 6 + 1 + 1 + 1 + 8) break;
             if (n < 12) break;
             size_t const seg = (n + 3) / 4;
-            // sizing pass: bits of each stream, all lanes
             u32 bits[4];
-            for (int k = 0; k < 4; k++) {
-                const u8* const s = src + (size_t)k * seg; size_t const len = (k < 3) ? seg : n - 3 * seg;
+            for (int k = 0; k < 4; k++) {      // sizing pass: bits of each stream, all lanes
+                const u8* const sk = src + (size_t)k * seg; size_t const len = (k < 3) ? seg : n - 3 * seg;
                 u32 b = 0;
-                for (size_t i = (size_t)w.lane; i < len; i += C::W) b += S.hufBits[s[i]];
+                for (size_t i = (size_t)w.lane; i < len; i += C::W) b += S.hufBits[sk[i]];
                 bits[k] = w.sum(b);
             }
-            size_t sz[4], off[4]; size_t acc = 6; bool fail = false;
+            size_t acc = 6; bool fail = false;
             for (int k = 0; k < 4; k++) {
-                sz[k] = ((size_t)bits[k] + 1 + 7) >> 3;
-                off[k] = acc;
-                // the reference encodes stream k into what is left of the buffer and gives up on overflow
-                size_t const capk = opcap - acc;
-                if (capk <= 8 || (((size_t)bits[k] + 1) >> 3) >= capk - 8) { fail = true; break; }
-                if (sz[k] > 65535) { fail = true; break; }
-                acc += sz[k];
-            }
-            if (fail) break;
-            for (int k = w.lane; k < 4; k += C::W) {
-                const u8* const s = src + (size_t)k * seg; size_t const len = (k < 3) ? seg : n - 3 * seg;
-                huf_encode_stream(S, op + off[k], opcap - off[k], s, len);
-                if (k < 3) { op[2 * k] = (u8)sz[k]; op[2 * k + 1] = (u8)(sz[k] >> 8); }
+                const u8* const sk = src + (size_t)k * seg; size_t const len = (k < 3) ? seg : n - 3 * seg;
+                // the reference encodes stream k into what is left of the buffer and gives up on overflow or > 65535 bytes
+                size_t const c = huf_encode_stream(w, S, op + acc, opcap - acc, sk, len, bits[k]);
+                if (c == 0 || c > 65535) { fail = true; break; }
+                if (k < 3 && w.lane == 0) { op[2 * k] = (u8)c; op[2 * k + 1] = (u8)(c >> 8); }
+                acc += c;
             }
             w.sync();
+            if (fail) break;
             total = hSize + acc;
         }
         if (total >= n - 1) break;     // HUF_compressCTable_internal :1237
@@ -1011,35 +1050,67 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
         if (type == 2) lastCountSize = c;
         op += c;
     }
+    // ZSTD_encodeSequences_body, zstd_compress_sequences.c:290-382, in two phases:
+    //  1. the three FSE state chains (LL, OF, ML) are independent of each other: lanes 0..2 walk one each,
+    //     last sequence to first, recording the bits every transition emits;
+    //  2. all lanes pack the per-sequence bit groups (state bits OF,ML,LL then extra bits LL,ML,OF) at
+    //     offsets from a prefix sum, the last lane appends the final states (ML,OF,LL) and the end mark.
+    if (w.lane == 0) *seqHead = (u8)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
     size_t streamSize = 0;
-    if (w.lane == 0) {   // ZSTD_encodeSequences_body, zstd_compress_sequences.c:290-382
-        *seqHead = (u8)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
-        size_t const capLeft = (size_t)(oend - op);
-        if (capLeft <= 8) streamSize = ERR(E_dstSize_tooSmall);
-        else {
-            BitW bw; bw.init(op, capLeft);
-            const FseCT& ctLL = S.ct[0]; const FseCT& ctOF = S.ct[1]; const FseCT& ctML = S.ct[2];
-            u32 n = nbSeq - 1;
-            u32 sML = fse_init_state2(ctML, mlc[n]), sOF = fse_init_state2(ctOF, ofc[n]), sLL = fse_init_state2(ctLL, llc[n]);
-            bw.add(W.seqLL[n], ZB_T.LL_bits[llc[n]]);
-            bw.add(W.seqML[n] - MINMATCH, ZB_T.ML_bits[mlc[n]]);
-            bw.add(W.seqOF[n], ofc[n]);
-            while (n-- > 0) {
-                sOF = fse_encode(bw, ctOF, sOF, ofc[n]);
-                sML = fse_encode(bw, ctML, sML, mlc[n]);
-                sLL = fse_encode(bw, ctLL, sLL, llc[n]);
-                bw.add(W.seqLL[n], ZB_T.LL_bits[llc[n]]);
-                bw.add(W.seqML[n] - MINMATCH, ZB_T.ML_bits[mlc[n]]);
-                bw.add(W.seqOF[n], ofc[n]);
+    {
+        u16* const stb = W.stbits;
+        for (int t = w.lane; t < 3; t += C::W) {
+            const u8* const codes = t == 0 ? llc : t == 1 ? ofc : mlc;
+            const FseCT& ct = S.ct[t];
+            u16* const out = stb + (size_t)t * MAX_SEQ;
+            u32 state = fse_init_state2(ct, codes[nbSeq - 1]);
+            for (u32 n = nbSeq - 1; n-- > 0;) {
+                SymTT const tt = ct.tt[codes[n]];
+                u32 const nb = (state + tt.deltaNbBits) >> 16;
+                out[n] = (u16)((state & ((1u << nb) - 1)) | (nb << 12));
+                state = ct.stateTable[(int)(state >> nb) + tt.deltaFindState];
             }
-            bw.add(sML, ctML.tableLog); bw.add(sOF, ctOF.tableLog); bw.add(sLL, ctLL.tableLog);
-            streamSize = bw.close();
-            if (streamSize == 0) streamSize = ERR(E_dstSize_tooSmall);
+            S.tmp[t] = state;
         }
+        w.sync();
+        u32 const B = (nbSeq + C::W - 1) / C::W;
+        u32 const j0 = (u32)w.lane * B < nbSeq ? (u32)w.lane * B : nbSeq;
+        u32 const j1 = j0 + B < nbSeq ? j0 + B : nbSeq;
+        u32 mine = 0;
+        for (u32 j = j0; j < j1; j++) {
+            u32 const n = nbSeq - 1 - j;
+            mine += ZB_T.LL_bits[llc[n]] + ZB_T.ML_bits[mlc[n]] + ofc[n];
+            if (j) mine += (stb[n] >> 12) + (stb[MAX_SEQ + n] >> 12) + (stb[2 * MAX_SEQ + n] >> 12);
+        }
+        u32 const start = w.exscan(mine);
+        u32 const seqBits = w.bcast(start + mine, C::W - 1);
+        size_t const totalBits = (size_t)seqBits + S.ct[0].tableLog + S.ct[1].tableLog + S.ct[2].tableLog + 1;
+        size_t const capLeft = (size_t)(oend - op);
+        if (capLeft <= 8 || (totalBits >> 3) >= capLeft - 8) return ERR(E_dstSize_tooSmall);
+        streamSize = (totalBits + 7) >> 3;
+        for (size_t i = (size_t)w.lane; i < streamSize; i += C::W) op[i] = 0;
+        w.sync();
+        LaneBits<C> lb; lb.init(op, start);
+        for (u32 j = j0; j < j1; j++) {
+            u32 const n = nbSeq - 1 - j;
+            if (j) {
+                u32 const o = stb[MAX_SEQ + n], m = stb[2 * MAX_SEQ + n], l = stb[n];
+                lb.add(w, o & 0xFFF, o >> 12); lb.add(w, m & 0xFFF, m >> 12); lb.add(w, l & 0xFFF, l >> 12);
+            }
+            u32 const lbits = ZB_T.LL_bits[llc[n]], mbits = ZB_T.ML_bits[mlc[n]], obits = ofc[n];
+            lb.add(w, W.seqLL[n] & ((1u << lbits) - 1), lbits);
+            lb.add(w, (W.seqML[n] - MINMATCH) & ((1u << mbits) - 1), mbits);
+            lb.add(w, W.seqOF[n] & (obits >= 32 ? 0xFFFFFFFFu : ((1u << obits) - 1)), obits);
+        }
+        if (w.lane == C::W - 1) {
+            lb.add(w, S.tmp[2] & ((1u << S.ct[2].tableLog) - 1), S.ct[2].tableLog);
+            lb.add(w, S.tmp[1] & ((1u << S.ct[1].tableLog) - 1), S.ct[1].tableLog);
+            lb.add(w, S.tmp[0] & ((1u << S.ct[0].tableLog) - 1), S.ct[0].tableLog);
+            lb.add(w, 1, 1);
+        }
+        lb.close(w);
+        w.sync();
     }
-    w.sync();
-    streamSize = w.bcast(streamSize);
-    if (isErr(streamSize)) return streamSize;
     op += streamSize;
     if (lastCountSize && (lastCountSize + streamSize) < 4) return 0;    // :2992-2998
     return (size_t)(op - dst);
@@ -1185,11 +1256,22 @@ ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, 
     if (nbSeq != PARSE_SKIPPED) {
         // gather literals (ZSTD_storeSeq copies them during the parse; the result is the same buffer)
         size_t litSize = 0;
-        {   size_t sp = 0;
-            for (u32 i = 0; i < nbSeq; i++) {
-                u32 const ll = W.seqLL[i];
-                for (u32 j = (u32)w.lane; j < ll; j += C::W) W.lit[litSize + j] = src[sp + j];
-                litSize += ll; sp += ll + W.seqML[i];
+        {   // 32 sequences per step: source / literal positions by prefix sums, short runs copied by the lane that
+            // owns the sequence, long runs by the whole group
+            size_t sp = 0;
+            for (u32 base = 0; base < nbSeq; base += C::W) {
+                u32 const i = base + (u32)w.lane;
+                u32 const ll = i < nbSeq ? W.seqLL[i] : 0, ml = i < nbSeq ? W.seqML[i] : 0;
+                u32 const lpre = w.exscan(ll), spre = w.exscan(ll + ml);
+                if (ll && ll <= 32) { u8* const d = W.lit + litSize + lpre; const u8* const f = src + sp + spre; for (u32 k = 0; k < ll; k++) d[k] = f[k]; }
+                u32 big = w.ballot(ll > 32);
+                while (big) {
+                    int const b = (int)ctz32(big); big &= big - 1;
+                    u32 const L = w.shfl(ll, b), lp = w.shfl(lpre, b), spp = w.shfl(spre, b);
+                    u8* const d = W.lit + litSize + lp; const u8* const f = src + sp + spp;
+                    for (u32 k = (u32)w.lane; k < L; k += C::W) d[k] = f[k];
+                }
+                litSize += w.bcast(lpre + ll, C::W - 1); sp += w.bcast(spre + ll + ml, C::W - 1);
             }
             for (u32 j = (u32)w.lane; j < lastLL; j += C::W) W.lit[litSize + j] = src[sp + j];
             litSize += lastLL;
