@@ -56,10 +56,13 @@ size_t zbe_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSi
     u8* in = (u8*)calloc(1, srcSize + 64);
     memcpy(in + 16, src, srcSize);
     // stage 1 on an 8-lane group (k_parse), stage 2 on a 32-lane warp (k_entropy), like the CUDA build
-    size_t results[32]; u32 nbSeqs[8], lastLLs[8];
-    run_warp<8>([&](const WarpEmuT<8>& w) { results[w.lane] = parse_stage(w, W, in + 16, srcSize, level, &nbSeqs[w.lane], &lastLLs[w.lane]); });
+    size_t results[32]; u32 nbSeqs[32], lastLLs[32];
+    const char* pl = getenv("ZB_EMU_PARSE_LANES");
+    int const lanes = pl ? atoi(pl) : 32;
+    if (lanes == 8) run_warp<8>([&](const WarpEmuT<8>& w) { results[w.lane] = parse_stage(w, W, in + 16, srcSize, level, &nbSeqs[w.lane], &lastLLs[w.lane]); });
+    else run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = parse_stage(w, W, in + 16, srcSize, level, &nbSeqs[w.lane], &lastLLs[w.lane]); });
     size_t r = results[0];
-    for (int i = 1; i < 8; i++) if (results[i] != r || nbSeqs[i] != nbSeqs[0] || lastLLs[i] != lastLLs[0]) r = ERR(E_GENERIC);
+    for (int i = 1; i < (lanes == 8 ? 8 : 32); i++) if (results[i] != r || nbSeqs[i] != nbSeqs[0] || lastLLs[i] != lastLLs[0]) r = ERR(E_GENERIC);
     if (!isErr(r)) {
         run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = encode_stage(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level, nbSeqs[0], lastLLs[0]); });
         r = results[0];

@@ -72,6 +72,8 @@ def hostsim():
         ("zbh_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
         ("zbh_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         ("zbh_compress_bound", C.c_size_t, [C.c_size_t]),
+        ("zbe_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("zbe_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     ])
     if L is None:
         raise RuntimeError(f"{HOSTSIM_PATH} missing: run __graft_entry__.build()")
@@ -114,6 +116,15 @@ def hostsim_compress(data: bytes, level: int = 3):
 
 def hostsim_decompress(frame: bytes, cap: int):
     return _call_d(hostsim().zbh_decompress, frame, cap)
+
+
+def emu_compress(data: bytes, level: int = 3):
+    """Kernel source on the emulated 32-lane warp (tests/hostsim/simt_emu.h)."""
+    return _call_c(hostsim().zbe_compress, data, level)
+
+
+def emu_decompress(frame: bytes, cap: int):
+    return _call_d(hostsim().zbe_decompress, frame, cap)
 
 
 def ref_stream_compress(data: bytes, level: int, slice_size: int = 131072, checksum: bool = False) -> bytes:

@@ -8,7 +8,8 @@ from pathlib import Path
 import pytest
 
 from tests import cases
-from tests.oracle_util import hostsim_compress, hostsim_decompress, oracle_compress, oracle_decompress, ref, ref_stream_compress
+from tests.oracle_util import (emu_compress, emu_decompress, hostsim_compress, hostsim_decompress, oracle_compress, oracle_decompress, ref,
+                               ref_stream_compress)
 
 GOLDEN = Path(__file__).parent / "golden"
 
@@ -62,3 +63,17 @@ def test_hostsim_decodes_reference_streams():
     for level in (3, 9):
         z = ref_stream_compress(data, level, checksum=True)
         assert hostsim_decompress(z, len(data)) == data
+
+
+@pytest.mark.parametrize("lanes", ["32", "8"])
+def test_simt_emulated_warp_matches_oracle(lanes, monkeypatch):
+    """The cooperative code paths (batch probing with match_any forwarding, ballots, prefix-summed bit packing,
+    in-order warp execution of sequences) on the fiber-based warp emulator, 32- and 8-lane parse groups."""
+    monkeypatch.setenv("ZB_EMU_PARSE_LANES", lanes)
+    todo = cases.special_cases() + cases.corpus_cases(16) + cases.edge_cases(classes=(0, 4), sizes=[0, 1, 7, 8, 64, 255, 256, 1000, 5000, 16385, 65536, 100000, 131071])
+    for level in (3, 1):
+        for name, data in todo:
+            exp = oracle_compress(data, level)
+            assert emu_compress(data, level) == exp, (name, level, lanes)
+            if lanes == "32":
+                assert emu_decompress(exp, len(data)) == data, (name, level)

@@ -279,9 +279,19 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
     u32 off1 = 1, off2 = 0;             // {1,4,8} clipped by maxRep = 1 at position 1 (zstd_double_fast.c:158-164)
     u32 nbSeq = 0;
     u32 const lane = (u32)w.lane;
+    bool rep2Pending = false;           // the "immediate repcode" test of :308-320 is due at ip (folded into the next batch)
     for (;;) {   // one iteration per stored match
         u32 step = 1; int nextStep = ip + 256, ip1 = ip + 1;
-        if (ip1 > ilimit) break;
+        if (ip1 > ilimit) {
+            // no search position left; the immediate-repcode loop may still fire at ip == ilimit
+            while (rep2Pending && (ip <= ilimit) && (off2 > 0) && (load32(src + ip) == load32(src + ip - (int)off2))) {
+                u32 const rLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)ip + 4 - off2) + 4;
+                u32 const t = off2; off2 = off1; off1 = t;
+                if (lane == 0) { W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength; }   // table writes are never read again
+                nbSeq++; ip += (int)rLength; anchor = ip;
+            }
+            break;
+        }
         u32 width = C::W < 4 ? C::W : 4;
         int ev = -1;                      // event lane
         // values of the batch that found the event (per lane)
@@ -295,6 +305,8 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             hl = hash8v(d8, hBitsL);
             u32 const hs = hashSv(d8, hBitsS, mls);
             u32 const tl = active ? hashLong[hl] : 0, ts = active ? hashSmall[hs] : 0;
+            // lane 0 sits at ip: fold the immediate-repcode test into this batch (its load overlaps the table loads)
+            bool const rep2Hit = rep2Pending && lane == 0 && off2 > 0 && (load32(src + p - (int)off2) == (u32)d8);
             u32 const mL = w.match_any(active ? hl : (0x80000000u | lane));
             u32 const mS = w.match_any(active ? hs : (0x80000000u | lane));
             u32 const below = (1u << lane) - 1;
@@ -308,7 +320,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
                 bool const repOk = (off1 > 0) && (load32(src + p + 1 - (int)off1) == (u32)(d8 >> 8));
                 bool const longOk = (idxl >= 2) && (load64(src + (idxl - 2)) == d8);
                 bool const shortOk = (idxs >= 2) && (load32(src + (idxs - 2)) == (u32)d8);
-                kind = repOk ? 1 : longOk ? 2 : shortOk ? 3 : 0;
+                kind = rep2Hit ? 4 : repOk ? 1 : longOk ? 2 : shortOk ? 3 : 0;
             }
             u32 const hm = w.ballot(kind != 0);
             nActive = popc32(w.ballot(active));
@@ -320,6 +332,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
                 if (!(mS & later)) hashSmall[hs] = (u32)p + 2;
             }
             w.sync();
+            rep2Pending = false;
             if (ev >= 0) break;
             // no match in this batch: continue after its last position
             {   int const L = (int)nActive - 1;
@@ -332,8 +345,17 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
         }
         if (ev < 0) break;
         // ---- event at lane ev: gather what the serial code would hold at this point
+        u32 const kinde = w.shfl(kind, ev);
+        if (kinde == 4) {   // immediate repcode at ip (lane 0): :308-320; its table writes were lane 0's commits
+            u32 const rLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)ip + 4 - off2) + 4;
+            u32 const t = off2; off2 = off1; off1 = t;
+            if (lane == 0) { W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength; }
+            nbSeq++; ip += (int)rLength; anchor = ip;
+            rep2Pending = true;
+            continue;
+        }
         int const pe = w.shfl(p, ev), p1e = w.shfl(p1, ev);
-        u32 const ste = w.shfl(st, ev), kinde = w.shfl(kind, ev), idxle = w.shfl(idxl, ev), idxse = w.shfl(idxs, ev);
+        u32 const ste = w.shfl(st, ev), idxle = w.shfl(idxl, ev), idxse = w.shfl(idxs, ev);
         bool const nextInBatch = (ev + 1 < (int)nActive);
         int const nl = nextInBatch ? ev + 1 : ev;
         u32 hl1 = w.shfl(hl, nl), idxl1 = w.shfl(idxl, nl); u64 d81 = w.shfl(d8, nl);
@@ -382,21 +404,9 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
                 hashSmall[hashSv(dA, hBitsS, mls)] = A + 2;
                 hashSmall[hashSv(dC, hBitsS, mls)] = (u32)ip - 1 + 2;
             }
-            w.sync();
-            while ((ip <= ilimit) && (off2 > 0) && (load32(src + ip) == load32(src + ip - (int)off2))) {   // :308-320
-                u32 const rLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)ip + 4 - off2) + 4;
-                u32 const t = off2; off2 = off1; off1 = t;
-                if (lane == 0) {
-                    u64 const d = load64(src + ip);
-                    hashSmall[hashSv(d, hBitsS, mls)] = (u32)ip + 2;
-                    hashLong[hash8v(d, hBitsL)] = (u32)ip + 2;
-                    W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength;
-                }
-                nbSeq++;
-                ip += (int)rLength; anchor = ip;
-                w.sync();
-            }
-        } else w.sync();
+            rep2Pending = true;
+        }
+        w.sync();
     }
     w.sync();
     *lastLL = (u32)(n - anchor);
