@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "../../zstd_jni_b200/csrc/zb_decode.cuh"
+#include "../../zstd_jni_b200/csrc/zb_decode_fast.cuh"
 #include "../../zstd_jni_b200/csrc/zb_encode.cuh"
 #include "simt_emu.h"
 
@@ -86,6 +87,41 @@ size_t zbe_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);
     if (!isErr(r)) memcpy(dst, out + 16, r);
     free(S); free(scratch); free(in); free(out);
+    return r;
+}
+
+// ---- the staged batch decoder (zb_decode_fast.cuh) on one item; emu != 0 runs stages A and D on the 32-lane emulator
+size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int emu) {
+    using namespace zb;
+    DecShared* S = (DecShared*)calloc(1, sizeof(DecShared));
+    u8* in = (u8*)calloc(1, srcSize + 64);
+    memcpy(in + 16, src, srcSize);
+    u8* out = (u8*)calloc(1, dstCapacity + 64);
+    u8* lit = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
+    u16* huf = (u16*)calloc(FAST_HUF_ENTRIES, 2);
+    u32* fse = (u32*)calloc(FAST_FSE_ENTRIES, 4);
+    u64* seqs = (u64*)calloc(FAST_MAXS + 8, 8);
+    DecDesc d;
+    size_t r;
+    if (emu) run_warp<32>([&](const WarpEmuT<32>& w) { dec_prepare(w, *S, in + 16, srcSize, dstCapacity, &d, huf, fse); });
+    else { WarpHost w; dec_prepare(w, *S, in + 16, srcSize, dstCapacity, &d, huf, fse); }
+    if (d.mode == 0) {
+        u8* scratch = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
+        WarpHost w; r = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch);
+        free(scratch);
+    } else {
+        const u8* blk = in + 16 + d.blockOff;
+        for (int k = 0; k < 4; k++) dec_huf(&d, k, blk, huf, lit);
+        dec_seq(&d, blk, fse, seqs);
+        if (emu) {
+            size_t results[32];
+            run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = dec_exec(w, &d, in + 16, lit, seqs, out + 16, dstCapacity); });
+            r = results[0];
+            for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);
+        } else { WarpHost w; r = dec_exec(w, &d, in + 16, lit, seqs, out + 16, dstCapacity); }
+    }
+    if (!isErr(r)) memcpy(dst, out + 16, r);
+    free(S); free(in); free(out); free(lit); free(huf); free(fse); free(seqs);
     return r;
 }
 

@@ -74,6 +74,7 @@ def hostsim():
         ("zbh_compress_bound", C.c_size_t, [C.c_size_t]),
         ("zbe_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
         ("zbe_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+        ("zbp_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
     ])
     if L is None:
         raise RuntimeError(f"{HOSTSIM_PATH} missing: run __graft_entry__.build()")
@@ -125,6 +126,13 @@ def emu_compress(data: bytes, level: int = 3):
 
 def emu_decompress(frame: bytes, cap: int):
     return _call_d(hostsim().zbe_decompress, frame, cap)
+
+
+def staged_decompress(frame: bytes, cap: int, emu: bool = False):
+    """The staged batch decoder (zb_decode_fast.cuh) on the host (1 lane) or on the 32-lane emulator."""
+    out = C.create_string_buffer(max(cap, 1))
+    n = hostsim().zbp_decompress(out, cap, frame, len(frame), 1 if emu else 0)
+    return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
 
 
 def ref_stream_compress(data: bytes, level: int, slice_size: int = 131072, checksum: bool = False) -> bytes:

@@ -125,6 +125,29 @@ def test_full_size_config_properties(ctx):
     assert oracle_decompress(stream[: offs[k]].tobytes(), k * 131072) == data[:k].tobytes()
 
 
+def test_staged_and_fused_decoders_agree(ctx):
+    """The staged batch decoder (default) and the fused kernel must return the same bytes and the same
+    error codes on a mixed bag: valid single-block frames, multi-block streams, corrupted frames."""
+    from zstd_jni_b200 import corpus
+    rng = np.random.default_rng(9)
+    blobs, caps = [], []
+    for i in range(48):
+        data = corpus.chunk(i)[: int(rng.integers(1, 131073))].tobytes()
+        z = oracle_compress(data, 3 if i % 3 else 1)
+        blobs.append(z); caps.append(len(data))
+        zz = bytearray(z); k = int(rng.integers(0, len(zz))); zz[k] ^= 1 << int(rng.integers(0, 8))
+        blobs.append(bytes(zz)); caps.append(len(data))
+        blobs.append(z); caps.append(max(0, len(data) - 3))
+    blobs.append(blobs[0] + blobs[3]); caps.append(caps[0] + caps[3])          # two frames in one item -> fused path
+    ctx.setOption("dec_pipeline", 1)
+    a = ctx.decompressBatch(blobs, caps, raise_on_error=False)
+    ctx.setOption("dec_pipeline", 0)
+    b = ctx.decompressBatch(blobs, caps, raise_on_error=False)
+    ctx.setOption("dec_pipeline", 1)
+    exp = [oracle_decompress(z, c) for z, c in zip(blobs, caps)]
+    assert a == exp and b == exp
+
+
 def test_device_resident_api(ctx):
     import torch
     from zstd_jni_b200 import _native, corpus

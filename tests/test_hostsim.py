@@ -77,3 +77,31 @@ def test_simt_emulated_warp_matches_oracle(lanes, monkeypatch):
             assert emu_compress(data, level) == exp, (name, level, lanes)
             if lanes == "32":
                 assert emu_decompress(exp, len(data)) == data, (name, level)
+
+
+@pytest.mark.parametrize("emu", [False, True])
+def test_staged_batch_decoder_matches_oracle(emu):
+    """zb_decode_fast.cuh (prepare -> Huffman streams -> sequence stream -> warp execution) on the host / the
+    32-lane emulator: round trips, golden streams (multi-block items fall back to the fused path) and the same
+    error code as the oracle on corrupted frames, whichever stage meets the damage."""
+    import numpy as np
+    from tests.oracle_util import staged_decompress
+    from zstd_jni_b200 import corpus
+    todo = cases.special_cases() + cases.corpus_cases(16) + cases.edge_cases(classes=(0, 2, 4, 5, 7), sizes=[0, 1, 7, 8, 64, 255, 256, 1000, 5000, 16385, 65536, 100000, 131071])
+    for level in (3, 1):
+        for name, data in todo:
+            assert staged_decompress(oracle_compress(data, level), len(data), emu) == data, (name, level)
+    man = json.loads((GOLDEN / "manifest.json").read_text())
+    for e in man["decode_only"] + man["errors"]:
+        blob = (GOLDEN / e["file"]).read_bytes(); cap = e.get("size", e.get("cap"))
+        assert staged_decompress(blob, cap, emu) == oracle_decompress(blob, cap), e["file"]
+    rng = np.random.default_rng(21 + emu)
+    for idx in (0, 1, 2, 4, 5, 7, 15, 23):
+        data = corpus.chunk(idx)[:60000].tobytes(); z = oracle_compress(data, 3)
+        for _ in range(40 if emu else 120):
+            zz = bytearray(z); k = int(rng.integers(0, len(zz))); zz[k] ^= 1 << int(rng.integers(0, 8))
+            if rng.random() < 0.2:
+                zz = zz[: int(rng.integers(1, len(zz)))]
+            for cap in (len(data), len(data) - 7):
+                a = oracle_decompress(bytes(zz), cap); b = staged_decompress(bytes(zz), cap, emu)
+                assert a == b, (idx, k, cap, a if isinstance(a, int) else "ok", b if isinstance(b, int) else "ok")

@@ -250,11 +250,21 @@ ZB_HDN bool huf_decode_stream(const u16* table, u32 log, const u8* src, size_t s
 }
 
 // ------------------------------------------------------- literals section
-// ZSTD_decodeLiteralsBlock, zstd_decompress_block.c:134-340.
-// On success: *litPtr/*litSize describe the literals; returns section size.
+// ZSTD_decodeLiteralsBlock, zstd_decompress_block.c:134-340, in two steps: parse_literals() reads the header
+// (and the Huffman table, into S.huf) and describes the streams; the symbols are decoded afterwards -- by
+// lanes 0..3 of the same warp in the fused kernel, by one thread per stream in the batch pipeline.
+struct LitInfo {
+    u32 mode;            // 0 = raw (bytes at rawOff), 1 = rle (rleByte), 2 = Huffman streams
+    u32 litSize;
+    u32 nStreams;        // 1 or 4 when mode == 2
+    u32 sOff[4], sLen[4];   // stream k: bytes [sOff, sOff+sLen) relative to the section start
+    u32 oOff[4], oCnt[4];   // its symbols land at [oOff, oOff+oCnt) of the literal buffer
+    u32 rawOff;
+    u32 rleByte;
+};
+
 template <class C>
-ZB_HDN size_t decode_literals(const C& w, DecShared& S, const u8* src, size_t srcSize, size_t blockSizeMax, size_t dstCapacity,
-                              u8* scratch, const u8** litPtr, size_t* litSizeOut) {
+ZB_HDN size_t parse_literals(const C& w, DecShared& S, const u8* src, size_t srcSize, size_t blockSizeMax, size_t dstCapacity, LitInfo* li) {
     size_t const expectedWrite = blockSizeMax < dstCapacity ? blockSizeMax : dstCapacity;
     if (srcSize < 2) return ERR(E_corruption_detected);
     u32 const b0 = src[0], type = b0 & 3, lhl = (b0 >> 2) & 3;
@@ -281,28 +291,21 @@ ZB_HDN size_t decode_literals(const C& w, DecShared& S, const u8* src, size_t sr
             p += h; c -= h;
         }
         // stream geometry (HUF_decompress4X1_usingDTable_internal_body :601-650)
-        bool ok = true;
-        size_t len[4], outN[4]; const u8* sp[4]; size_t seg = 0; int nStreams = 1;
-        if (single) { sp[0] = p; len[0] = c; outN[0] = litSize; }
+        li->mode = 2; li->litSize = (u32)litSize;
+        u32 const pOff = (u32)(p - src);
+        if (single) { li->nStreams = 1; li->sOff[0] = pOff; li->sLen[0] = (u32)c; li->oOff[0] = 0; li->oCnt[0] = (u32)litSize; }
         else {
-            nStreams = 4;
+            li->nStreams = 4;
             if (c < 10 || litSize < 6) return ERR(E_corruption_detected);
             size_t const l1 = load16(p), l2 = load16(p + 2), l3 = load16(p + 4);
             if (l1 + l2 + l3 + 6 > c) return ERR(E_corruption_detected);
-            seg = (litSize + 3) / 4;
+            size_t const seg = (litSize + 3) / 4;
             if (3 * seg > litSize) return ERR(E_corruption_detected);
-            sp[0] = p + 6; sp[1] = sp[0] + l1; sp[2] = sp[1] + l2; sp[3] = sp[2] + l3;
-            len[0] = l1; len[1] = l2; len[2] = l3; len[3] = c - (l1 + l2 + l3 + 6);
-            outN[0] = outN[1] = outN[2] = seg; outN[3] = litSize - 3 * seg;
+            li->sOff[0] = pOff + 6; li->sOff[1] = li->sOff[0] + (u32)l1; li->sOff[2] = li->sOff[1] + (u32)l2; li->sOff[3] = li->sOff[2] + (u32)l3;
+            li->sLen[0] = (u32)l1; li->sLen[1] = (u32)l2; li->sLen[2] = (u32)l3; li->sLen[3] = (u32)(c - (l1 + l2 + l3 + 6));
+            for (int k = 0; k < 4; k++) { li->oOff[k] = (u32)(k * seg); li->oCnt[k] = (u32)(k < 3 ? seg : litSize - 3 * seg); }
         }
-        // lanes 0..3 decode one stream each (all of them on a 1-lane host context)
-        for (int k = w.lane; k < nStreams; k += C::W)
-            ok = huf_decode_stream(S.huf, S.hufLog, sp[k], len[k], scratch + (size_t)k * seg, outN[k]) && ok;
-        bool const allOk = (w.ballot(!ok) == 0);
-        w.sync();
-        if (!allOk) return ERR(E_corruption_detected);
-        S.litEntropy = 1;
-        *litPtr = scratch; *litSizeOut = litSize;
+        if (w.lane == 0) S.litEntropy = 1;
         return litCSize + lhSize;
     }
     size_t lhSize, litSize;
@@ -317,33 +320,46 @@ ZB_HDN size_t decode_literals(const C& w, DecShared& S, const u8* src, size_t sr
     }
     if (litSize > blockSizeMax) return ERR(E_corruption_detected);
     if (expectedWrite < litSize) return ERR(E_dstSize_tooSmall);
+    li->litSize = (u32)litSize; li->nStreams = 0;
     if (type == 0) {
         if (litSize + lhSize > srcSize) return ERR(E_corruption_detected);
-        *litPtr = src + lhSize; *litSizeOut = litSize;
+        li->mode = 0; li->rawOff = (u32)lhSize;
         return lhSize + litSize;
     }
-    {   u8 const v = src[lhSize];
-        for (size_t k = (size_t)w.lane; k < litSize; k += C::W) scratch[k] = v;
-        w.sync();
-    }
-    *litPtr = scratch; *litSizeOut = litSize;
+    li->mode = 1; li->rleByte = src[lhSize];
     return lhSize + 1;
 }
 
-// --------------------------------------------------- one compressed block
-// ZSTD_decompressBlock_internal :2066-2174.  `frameStart` is the first output byte of
-// the frame (offsets may reach back that far); writes at op, at most `cap` bytes.
+// fused variant: literals end up readable at *litPtr (in place for raw, `scratch` otherwise)
 template <class C>
-ZB_HDN size_t decode_block(const C& w, DecShared& S, const u8* frameStart, u8* op0, size_t cap,
-                           const u8* src, size_t srcSize, size_t blockSizeMax, u8* scratch) {
-    if (srcSize > blockSizeMax) return ERR(E_srcSize_wrong);
-    const u8* ip = src; size_t left = srcSize;
-    const u8* lit = nullptr; size_t litSize = 0;
-    {   size_t const r = decode_literals(w, S, ip, left, blockSizeMax, cap, scratch, &lit, &litSize);
-        if (isErr(r)) return r;
-        ip += r; left -= r;
+ZB_HDN size_t decode_literals(const C& w, DecShared& S, const u8* src, size_t srcSize, size_t blockSizeMax, size_t dstCapacity,
+                              u8* scratch, const u8** litPtr, size_t* litSizeOut) {
+    LitInfo li;
+    bool const hadEntropy = S.litEntropy != 0;
+    size_t const r = parse_literals(w, S, src, srcSize, blockSizeMax, dstCapacity, &li);
+    if (isErr(r)) return r;
+    *litSizeOut = li.litSize;
+    if (li.mode == 0) { *litPtr = src + li.rawOff; return r; }
+    if (li.mode == 1) {
+        u8 const v = (u8)li.rleByte;
+        for (size_t k = (size_t)w.lane; k < li.litSize; k += C::W) scratch[k] = v;
+        w.sync();
+        *litPtr = scratch; return r;
     }
-    // sequences header (ZSTD_decodeSeqHeaders :695-775): lane 0 parses, lanes 0..2 build
+    bool ok = true;   // lanes 0..3 decode one stream each (all of them on a 1-lane host context)
+    for (int k = w.lane; k < (int)li.nStreams; k += C::W)
+        ok = huf_decode_stream(S.huf, S.hufLog, src + li.sOff[k], li.sLen[k], scratch + li.oOff[k], li.oCnt[k]) && ok;
+    bool const allOk = (w.ballot(!ok) == 0);
+    w.sync();
+    if (!allOk) { if (w.lane == 0 && !hadEntropy) S.litEntropy = 0; w.sync(); return ERR(E_corruption_detected); }
+    *litPtr = scratch;
+    return r;
+}
+
+// Sequences section header (ZSTD_decodeSeqHeaders :695-775) + table construction (ZSTD_buildSeqTable :647-693):
+// lane 0 parses, lanes 0..2 build one table each into S.fse[] / S.fseLog[].  Returns bytes consumed.
+template <class C>
+ZB_HDN size_t parse_seq_section(const C& w, DecShared& S, const u8* ip, size_t left, size_t cap, int* nbSeqOut) {
     size_t hdr = 0; int nbSeq = 0;
     if (w.lane == 0) {
         do {
@@ -384,7 +400,6 @@ ZB_HDN size_t decode_block(const C& w, DecShared& S, const u8* frameStart, u8* o
     w.sync();
     hdr = w.bcast(hdr); nbSeq = w.bcast(nbSeq);
     if (isErr(hdr)) return hdr;
-    ip += hdr; left -= hdr;
     if (nbSeq) {
         if (cap == 0) return ERR(E_dstSize_tooSmall);
         // table construction: one lane per table (ZSTD_buildSeqTable :647-693)
@@ -403,6 +418,27 @@ ZB_HDN size_t decode_block(const C& w, DecShared& S, const u8* frameStart, u8* o
         }
         w.sync();
     }
+    *nbSeqOut = nbSeq;
+    return hdr;
+}
+
+// --------------------------------------------------- one compressed block
+// ZSTD_decompressBlock_internal :2066-2174.  `frameStart` is the first output byte of
+// the frame (offsets may reach back that far); writes at op, at most `cap` bytes.
+template <class C>
+ZB_HDN size_t decode_block(const C& w, DecShared& S, const u8* frameStart, u8* op0, size_t cap,
+                           const u8* src, size_t srcSize, size_t blockSizeMax, u8* scratch) {
+    if (srcSize > blockSizeMax) return ERR(E_srcSize_wrong);
+    const u8* ip = src; size_t left = srcSize;
+    const u8* lit = nullptr; size_t litSize = 0;
+    {   size_t const r = decode_literals(w, S, ip, left, blockSizeMax, cap, scratch, &lit, &litSize);
+        if (isErr(r)) return r;
+        ip += r; left -= r;
+    }
+    int nbSeq = 0;
+    {   size_t const hdr = parse_seq_section(w, S, ip, left, cap, &nbSeq);
+        if (isErr(hdr)) return hdr;
+        ip += hdr; left -= hdr; }
 
     u8* op = op0; u8* const oend = op0 + cap;   // like the reference, a block is bounded by the destination only
     const u8* const litEnd = lit + litSize;

@@ -280,6 +280,10 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
     u32 nbSeq = 0;
     u32 const lane = (u32)w.lane;
     bool rep2Pending = false;           // the "immediate repcode" test of :308-320 is due at ip (folded into the next batch)
+    // Every speculative probe costs ~200 B of random HBM traffic (two table sectors read and written back, two or
+    // three candidate sectors), and probes behind the first hit are wasted.  The first batch of a search phase is
+    // therefore sized from a running estimate of how many positions recent phases needed; it doubles on a miss.
+    u32 est4 = 4 * 3;                   // estimate x4 (fixed point)
     for (;;) {   // one iteration per stored match
         u32 step = 1; int nextStep = ip + 256, ip1 = ip + 1;
         if (ip1 > ilimit) {
@@ -292,7 +296,10 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             }
             break;
         }
-        u32 width = C::W < 4 ? C::W : 4;
+        u32 width = 1;
+        {   u32 const want = (est4 + 3) / 4;
+            while (width < want && width < (u32)C::W) width *= 2; }
+        u32 runPos = 0;                   // positions searched in this phase
         int ev = -1;                      // event lane
         // values of the batch that found the event (per lane)
         int p = 0, p1 = 0; u32 st = 1; int ns = 0; u64 d8 = 0; u32 hl = 0, idxl = 0, idxs = 0, kind = 0, nActive = 0;
@@ -333,6 +340,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             }
             w.sync();
             rep2Pending = false;
+            runPos += (ev >= 0) ? (u32)ev + 1 : nActive;
             if (ev >= 0) break;
             // no match in this batch: continue after its last position
             {   int const L = (int)nActive - 1;
@@ -344,6 +352,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             width = width * 2 < (u32)C::W ? width * 2 : (u32)C::W;
         }
         if (ev < 0) break;
+        est4 = (3 * est4 + 4 * (runPos < 64 ? runPos : 64)) / 4;
         // ---- event at lane ev: gather what the serial code would hold at this point
         u32 const kinde = w.shfl(kind, ev);
         if (kinde == 4) {   // immediate repcode at ip (lane 0): :308-320; its table writes were lane 0's commits
