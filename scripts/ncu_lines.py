@@ -17,14 +17,14 @@ for l in dis.split("\n"):
     if m: fil = m.group(1).split("/")[-1]; line = int(m.group(2)); continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?)\s*;", l)
     if m and cur is not None: cur.append((re.sub(r"\s+", " ", m.group(2)).strip(), fil, line))
-name = [k for k in funcs if kname in k and len(funcs[k]) > 50][0]
-ins = funcs[name]
+cands = [k for k in funcs if kname in k and len(funcs[k]) > 50]
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(sass.split("\n")))
 hdr = rows[1]; si = hdr.index("Warp Stall Sampling (All Samples)"); ii = hdr.index("Instructions Executed")
 ncu = [(re.sub(r"\s+", " ", r[1]).strip(), int(r[si] or 0), int(r[ii] or 0)) for r in rows[2:] if len(r) > ii and r[si].isdigit()]
-print("sass rows", len(ncu), "disasm rows", len(ins), file=sys.stderr)
-assert len(ncu) == len(ins), "instruction count mismatch: rebuild the .so that was profiled"
+match = [k for k in cands if len(funcs[k]) == len(ncu)]
+assert match, "no function named *%s* has %d instructions (have %s): rebuild the .so that was profiled" % (kname, len(ncu), [len(funcs[k]) for k in cands])
+ins = funcs[match[0]]
 agg = collections.Counter(); aggi = collections.Counter()
 for (t, s, i), (t2, fl, ln) in zip(ncu, ins):
     agg[(fl, ln)] += s; aggi[(fl, ln)] += i

@@ -234,16 +234,22 @@ ZB_HDN bool huf_decode_stream(const u16* table, u32 log, const u8* src, size_t s
     i64 pos = (i64)(srcSize - 1) * 8 + highbit32(lastByte);
     size_t i = 0;
     u32 const mask = (1u << log) - 1;
+    // up to 4 symbols per refill (57-bit window just below `pos`); whole groups of 4 leave as one aligned 32-bit store
+    u32 lead = (u32)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
     while (i < n) {
-        // up to 4 symbols per refill: 57-bit window just below `pos`
         u64 const win = peek_bits(src, pos - 57, 57);
-        u32 used = 0;
-        for (int k = 0; k < 4 && i < n; k++) {
+        u32 used = 0, pack = 0; int c = 0;
+        int const lim = lead ? (int)lead : 4;
+        for (; c < lim && i + (size_t)c < n; c++) {
             u32 const idx = (u32)(win >> (57 - used - log)) & mask;
             u16 const e = table[idx];
-            dst[i++] = (u8)e;
+            pack |= (u32)(e & 0xFF) << (8 * c);
             used += e >> 8;
         }
+        if (c == 4 && !lead) *reinterpret_cast<u32*>(dst + i) = pack;
+        else for (int k = 0; k < c; k++) dst[i + (size_t)k] = (u8)(pack >> (8 * k));
+        lead = 0;
+        i += (size_t)c;
         pos -= used;
     }
     return pos == 0;
