@@ -99,7 +99,7 @@ size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     u8* out = (u8*)calloc(1, dstCapacity + 64);
     u8* lit = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
     u16* huf = (u16*)calloc(FAST_HUF_ENTRIES, 2);
-    u64* fse = (u64*)calloc(FAST_FSE_ENTRIES, 8);
+    u32* fse = (u32*)calloc(FAST_FSE_ENTRIES, 4);
     u64* seqs = (u64*)calloc(FAST_MAXS + 8, 8);
     DecDesc d;
     size_t r;
@@ -112,7 +112,7 @@ size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     } else {
         const u8* blk = in + 16 + d.blockOff;
         for (int k = 0; k < 4; k++) dec_huf(&d, k, blk, huf, lit);
-        dec_seq(&d, blk, fse, seqs);
+        dec_seq(&d, blk, fse, &h_tables, seqs);
         if (emu) {
             size_t results[32];
             run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = dec_exec(w, &d, in + 16, lit, seqs, out + 16, dstCapacity); });

@@ -25,7 +25,8 @@ namespace zb {
 
 constexpr u32 FAST_MAXS = 43776;            // > 131072 / MINMATCH: more sequences cannot fit a 128 KB block
 constexpr u32 FAST_HUF_ENTRIES = 1u << HUF_TABLELOG_MAX;
-constexpr u32 FAST_FSE_ENTRIES = 3 * 512;          // u64 entries: baseValue | nextState << 32 | nbBits << 48 | nbAddBits << 56
+constexpr u32 FAST_FSE_ENTRIES = 512 + 256 + 512;  // LL | OF | ML, packed u32 entries nextState | nbBits << 16 | symbol << 24
+constexpr u32 FAST_FSE_OF = 512, FAST_FSE_ML = 768;
 
 struct DecDesc {
     u32 mode;            // 0 = not eligible (fused kernel handles the item), 1 = compressed block, 2 = raw block, 3 = rle block
@@ -43,7 +44,7 @@ struct DecDesc {
 // ---------------------------------------------------------------------------------------- stage A
 // All lanes of a warp; S is the warp's shared scratch; tables are copied out to hufOut / fseOut.
 template <class C>
-ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize, size_t dstCapacity, DecDesc* d, u16* hufOut, u64* fseOut) {
+ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize, size_t dstCapacity, DecDesc* d, u16* hufOut, u32* fseOut) {
     DecDesc L;   // built in registers/local, stored by lane 0 at the end
     L.mode = 0; L.stA1 = L.stB = L.stA2 = L.stC = L.stD = 0; L.regen = 0; L.nbSeq = 0; L.litMode = 0; L.litSize = 0; L.nStreams = 0;
     L.blockOff = L.cSize = L.contentSize = L.rawOff = L.rleByte = L.hufLog = L.seqOff = L.seqLen = L.logLL = L.logOF = L.logML = 0;
@@ -89,12 +90,8 @@ ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize,
             L.logLL = S.fseLog[0]; L.logOF = S.fseLog[1]; L.logML = S.fseLog[2];
             for (int t = 0; t < 3; t++) {
                 u32 const nE = 1u << S.fseLog[t];
-                for (u32 i = (u32)w.lane; i < nE; i += C::W) {     // expand to self-contained entries (no code-table lookups in stage C)
-                    u32 const e = S.fse[t][i], sym = e >> 24;
-                    u32 const base = t == 0 ? ZB_T.LL_base[sym] : t == 2 ? ZB_T.ML_base[sym] : (sym < 2 ? sym : (1u << sym) - 3);
-                    u32 const add = t == 0 ? ZB_T.LL_bits[sym] : t == 2 ? ZB_T.ML_bits[sym] : sym;
-                    fseOut[t * 512 + i] = (u64)base | ((u64)(e & 0xFFFF) << 32) | ((u64)((e >> 16) & 0xFF) << 48) | ((u64)add << 56);
-                }
+                u32* const out = fseOut + (t == 0 ? 0 : t == 1 ? FAST_FSE_OF : FAST_FSE_ML);
+                for (u32 i = (u32)w.lane; i < nE; i += C::W) out[i] = S.fse[t][i];
             }
         }
     } while (0);
@@ -115,11 +112,13 @@ ZB_HDN void dec_huf(DecDesc* d, int k, const u8* blk, const u16* huf, u8* lit) {
 // repcode history {1,4,8}; sequences are stored as litLength | matchLength << 18 | offset << 36 (each < 2^18
 // for a block of at most 128 KB; larger values can only come from corrupt input and are clamped to 2^18-1 /
 // 2^28-1, which the executor rejects exactly like the originals).
-ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u64* fse, u64* seqOut) {
+// `fse` = the frame's three tables (FAST_FSE_ENTRIES u32, in shared memory on the GPU), `ct` = code tables
+// (shared memory copy on the GPU: per-lane indices would serialise in the constant cache).
+ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables* ct, u64* seqOut) {
     if (d->mode != 1 || d->stA1 || d->stA2 || d->nbSeq == 0) return;
     const u8* const ip = blk + d->seqOff; size_t const left = d->seqLen;
     if (left < 1 || ip[left - 1] == 0) { d->stC = E_corruption_detected; return; }
-    const u64* const tLL = fse; const u64* const tOF = fse + 512; const u64* const tML = fse + 1024;
+    const u32* const tLL = fse; const u32* const tOF = fse + FAST_FSE_OF; const u32* const tML = fse + FAST_FSE_ML;
     i64 pos = (i64)(left - 1) * 8 + highbit32(ip[left - 1]);
     u32 rep0 = 1, rep1 = 4, rep2 = 8;
     u32 const logLL = d->logLL, logOF = d->logOF, logML = d->logML;
@@ -128,25 +127,26 @@ ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u64* fse, u64* seqOut) {
     pos -= logML; u32 sML = (u32)peek_bits(ip, pos, logML);
     u32 const nbSeq = d->nbSeq;
     for (u32 k = 0; k < nbSeq; k++) {
-        u64 const eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
-        u32 const llBits = (u32)(eLL >> 56), mlBits = (u32)(eML >> 56), ofBits = (u32)(eOF >> 56);
-        u32 const nLL = (u32)(eLL >> 48) & 0xFF, nML = (u32)(eML >> 48) & 0xFF, nOF = (u32)(eOF >> 48) & 0xFF;
+        u32 const eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
+        u32 const llc = eLL >> 24, ofc = eOF >> 24, mlc = eML >> 24;
+        u32 const llBits = ct->LL_bits[llc], mlBits = ct->ML_bits[mlc], ofBits = ofc;
+        u32 const nLL = (eLL >> 16) & 0xFF, nML = (eML >> 16) & 0xFF, nOF = (eOF >> 16) & 0xFF;
         bool const lastSeq = (k + 1 == nbSeq);
-        u32 const ofRead = ofBits > 1 ? ofBits : ofBits;          // code 1 reads its single bit too
-        u32 const t1 = ofRead + mlBits + llBits, t2 = lastSeq ? 0 : nLL + nML + nOF;
+        u32 const t1 = ofBits + mlBits + llBits, t2 = lastSeq ? 0 : nLL + nML + nOF;
         // read order below `pos`: offset bits, ML extra, LL extra, then LL / ML / OF state bits
         u64 x; u32 y;
         if (t1 + t2 <= 57) { u64 const v = peek_bits(ip, pos - (i64)(t1 + t2), t1 + t2); x = v >> t2; y = (u32)(v & ((1ull << t2) - 1)); }
         else if (t1 <= 57) { x = peek_bits(ip, pos - (i64)t1, t1); y = (u32)peek_bits(ip, pos - (i64)(t1 + t2), t2); }
-        else { x = (peek_bits(ip, pos - (i64)ofRead, ofRead) << (mlBits + llBits)) | peek_bits(ip, pos - (i64)t1, mlBits + llBits); y = (u32)peek_bits(ip, pos - (i64)(t1 + t2), t2); }
+        else { x = (peek_bits(ip, pos - (i64)ofBits, ofBits) << (mlBits + llBits)) | peek_bits(ip, pos - (i64)t1, mlBits + llBits); y = (u32)peek_bits(ip, pos - (i64)(t1 + t2), t2); }
         pos -= (i64)(t1 + t2);
         u32 const ofVal = (u32)(x >> (mlBits + llBits));
-        u32 const matchLength = (u32)eML + (u32)((x >> llBits) & ((1ull << mlBits) - 1));
-        u32 const litLength = (u32)eLL + (u32)(x & ((1ull << llBits) - 1));
+        u32 const llBase = ct->LL_base[llc];
+        u32 const matchLength = ct->ML_base[mlc] + (u32)((x >> llBits) & ((1ull << mlBits) - 1));
+        u32 const litLength = llBase + (u32)(x & ((1ull << llBits) - 1));
         u32 offset;
-        if (ofBits > 1) { offset = (u32)eOF + ofVal; rep2 = rep1; rep1 = rep0; rep0 = offset; }
+        if (ofBits > 1) { offset = ((1u << ofBits) - 3) + ofVal; rep2 = rep1; rep1 = rep0; rep0 = offset; }
         else {
-            u32 const ll0 = ((u32)eLL == 0);       // baseValue == 0 (ZSTD_decodeSequence :1300)
+            u32 const ll0 = (llBase == 0);          // ZSTD_decodeSequence :1300 tests the base value
             if (ofBits == 0) { offset = ll0 ? rep1 : rep0; rep1 = ll0 ? rep0 : rep1; rep0 = offset; }
             else {
                 u32 const idx = 1 + ll0 + ofVal;
@@ -157,9 +157,9 @@ ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u64* fse, u64* seqOut) {
             }
         }
         if (!lastSeq) {
-            sLL = ((u32)(eLL >> 32) & 0xFFFF) + (y >> (nML + nOF));
-            sML = ((u32)(eML >> 32) & 0xFFFF) + ((y >> nOF) & ((1u << nML) - 1));
-            sOF = ((u32)(eOF >> 32) & 0xFFFF) + (y & ((1u << nOF) - 1));
+            sLL = (eLL & 0xFFFF) + (y >> (nML + nOF));
+            sML = (eML & 0xFFFF) + ((y >> nOF) & ((1u << nML) - 1));
+            sOF = (eOF & 0xFFFF) + (y & ((1u << nOF) - 1));
         }
         u64 const l = litLength > 0x3FFFF ? 0x3FFFF : litLength, m = matchLength > 0x3FFFF ? 0x3FFFF : matchLength;
         u64 const o = offset > 0xFFFFFFFu ? 0xFFFFFFFu : offset;
