@@ -214,6 +214,7 @@ def main():
     import torch.distributed as dist
     from zstd_jni_b200 import _native
     from zstd_jni_b200.zstd import ZstdBatchContext
+    from zstd_jni_b200 import sharding
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU fallback); use --impl reference for the CPU arm"
     torch.cuda.set_device(local)
     if world > 1:
@@ -233,7 +234,7 @@ def main():
     d_ooff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     d_back = torch.empty(n * CHUNK, dtype=torch.uint8, device=dev)
     d_res = torch.zeros(n, dtype=torch.int64, device=dev)
-    gathered = [torch.zeros(n, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+    index = {}
     stream = torch.cuda.Stream(device=dev)
     st = stream.cuda_stream
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -249,7 +250,8 @@ def main():
         if events: events[1].record(stream)
         check(L.zstdb200_compact_device(ctx.handle, n, d_slots.data_ptr(), stride, d_sizes.data_ptr(), d_out.data_ptr(), d_ooff.data_ptr(), st))
         if world > 1:
-            dist.all_gather(gathered, d_sizes)            # global stream index (8 B x frames); the only exchange
+            # global stream index (8 B x frames over NCCL); the only exchange on this path
+            index["offsets"] = sharding.global_offsets(sharding.gather_sizes(d_sizes, world * n))
         if events: events[2].record(stream)
         check(L.zstdb200_decompress_device(ctx.handle, n, d_out.data_ptr(), d_ooff.data_ptr(), d_back.data_ptr(), d_off.data_ptr(), d_res.data_ptr(), st))
         if events: events[3].record(stream)
@@ -267,6 +269,8 @@ def main():
         csize = int(d_sizes.sum().item())
         sampler = ClockSampler(local); sampler.start()
         launches0 = ctx.kernelLaunches()
+        ctx.setOption("timing", 1)          # the library brackets every kernel with CUDA events on its launching stream
+        ctx.kernelTimes()
         evs = [[ev() for _ in range(4)] for _ in range(args.steps)]
         barrier()
         t_begin, t_end = ev(), ev()
@@ -276,6 +280,8 @@ def main():
         t_end.record(stream)
         barrier()
         launches = ctx.kernelLaunches() - launches0
+        ktimes = ctx.kernelTimes()
+        ctx.setOption("timing", 0)
         clocks = sampler.stop()
     total_ms = t_begin.elapsed_time(t_end)
     k_comp = float(np.mean([e[0].elapsed_time(e[1]) for e in evs])); k_pack = float(np.mean([e[1].elapsed_time(e[2]) for e in evs])); k_dec = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
@@ -317,17 +323,26 @@ def main():
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
     algo_bytes = U + csize                                  # uncompressed + compressed bytes of every frame in the launch
-    kernels = {"k_compress": k_comp, "k_scan_sizes+k_compact": k_pack, "k_decompress": k_dec}
+    # per-kernel averages over the timed region (rank 0), from the events the library records around every launch
+    kernels = {k: v[0] for k, v in ktimes.items()}
+    phases = {"compress": k_comp, "scan+compact": k_pack, "decompress": k_dec}          # API-call brackets, max over ranks
     dom = max(kernels, key=kernels.get)
-    def roof(ms, extra=0):
-        a = (algo_bytes + extra) / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None}
+    traffic = {}
+    tpath = ROOT / "profiles" / "dram_traffic.json"          # dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)
+    if tpath.exists():
+        tj = json.loads(tpath.read_text())
+        if tj.get("chunks_per_gpu") == n and tj.get("level") == args.level:
+            traffic = tj.get("kernels", {})
+    def roof(name):
+        a = algo_bytes / (kernels[name] * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": traffic.get(name)}
     out = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
            "compress_gbs": world * U / ((k_comp + k_pack) * 1e-3) / 1e9, "decompress_gbs": world * U / (k_dec * 1e-3) / 1e9, "ratio": U / csize,
-           "kernel_ms": kernels, "roofline": dict(roof(kernels[dom]), kernel=dom, peak_source=peak_src,
-                                                  algorithmic_bytes_per_launch=algo_bytes),
-           "roofline_all": {k: roof(v) for k, v in kernels.items()},
+           "kernel_ms": kernels, "phase_ms": phases,
+           "roofline": dict(roof(dom), kernel=dom, peak_source=peak_src, algorithmic_bytes_per_launch=algo_bytes,
+                            launches_timed=ktimes[dom][1]),
+           "roofline_all": {k: roof(k) for k in kernels},
            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": U + csize, "d2h_bytes_per_step": csize + U, "ms_per_step": float(te.item()) * 1e3,
                    "api": "zstdb200_compress_chunks + zstdb200_decompress_frames, pinned host buffers"},
            "gpu_launches": int(launches), "clocks": clocks}

@@ -133,9 +133,13 @@ ZSTDB200_API void zstdb200_free(zstdb200_ctx* ctx);
 ZSTDB200_API const char* zstdb200_last_error(void);          /* thread-local text of the last CUDA/runtime failure */
 ZSTDB200_API int zstdb200_device_count(void);
 /* tuning knobs (also read from the environment at context creation):
- *   "enc_warps_per_sm" / ZSTDB200_ENC_WARPS_PER_SM, "dec_warps_per_sm" / ZSTDB200_DEC_WARPS_PER_SM */
+ *   "enc_warps_per_sm" / ZSTDB200_ENC_WARPS_PER_SM, "dec_warps_per_sm" / ZSTDB200_DEC_WARPS_PER_SM,
+ *   "parse_lanes" (4|8|16|32), "parse_blocks_per_sm", "dec_pipeline" (0|1), "host_slices", "timing" (0|1) */
 ZSTDB200_API int zstdb200_set_option(zstdb200_ctx* ctx, const char* name, long long value);
 ZSTDB200_API unsigned long long zstdb200_kernel_launches(const zstdb200_ctx* ctx);   /* kernels launched so far */
+/* with option "timing" = 1 every kernel launch is bracketed by CUDA events on its stream; this returns the averages
+ * since the previous call as "name:ms:count;..." (synchronises).  Used by bench.py for the roofline line. */
+ZSTDB200_API size_t zstdb200_kernel_times(zstdb200_ctx* ctx, char* buf, size_t cap);
 
 /* Host-memory batch calls (H2D, kernels, D2H inside the call; synchronous).
  * compress_chunks: `src` is cut into ceil(srcSize/chunkSize) chunks (chunkSize <= 131072); chunk i becomes

@@ -233,6 +233,15 @@ ZB_HD u32 hashSv(u64 d, u32 hBits, u32 mls) {
     case 7: return (u32)(((d << 8) * 58295818150454627ULL) >> (64 - hBits));
     }
 }
+// Private table cell of the cooperative parser: index (position + 2, < 2^18) | 14-bit fingerprint << 18 of the bytes
+// the reference would compare at that position (8 for the long table, 4 for the short one).  A fingerprint mismatch
+// proves the compare would fail, so the candidate bytes -- a random 32-byte HBM sector -- are not fetched at all;
+// decisions are unchanged.  Zero still means "empty".
+constexpr u32 CELL_IDX_MASK = 0x3FFFF;
+ZB_HD u32 tag8(u64 d) { return (u32)((d * 0x9E3779B97F4A7C15ULL) >> 50); }
+ZB_HD u32 tag4(u32 d) { return (d * 2246822519U) >> 18; }
+ZB_HD u32 cell(u32 idx, u32 tag) { return idx | (tag << 18); }
+
 // common prefix length of src[a..n) and src[b..) (b < a), all lanes cooperate; uniform result
 template <class C>
 ZB_HD u32 wcount(const C& w, const u8* src, u32 n, u32 a, u32 b) {
@@ -302,7 +311,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
         u32 runPos = 0;                   // positions searched in this phase
         int ev = -1;                      // event lane
         // values of the batch that found the event (per lane)
-        int p = 0, p1 = 0; u32 st = 1; int ns = 0; u64 d8 = 0; u32 hl = 0, idxl = 0, idxs = 0, kind = 0, nActive = 0;
+        int p = 0, p1 = 0; u32 st = 1; int ns = 0; u64 d8 = 0; u32 hl = 0, idxl = 0, idxs = 0, kind = 0, nActive = 0; bool plausL = false;
         for (;;) {   // batches of `width` consecutive search positions
             p = ip; p1 = ip1; st = step; ns = nextStep;
             if (step == 1 && ip + (int)width + 1 < nextStep) { p = ip + (int)lane; p1 = p + 1; }
@@ -312,6 +321,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             hl = hash8v(d8, hBitsL);
             u32 const hs = hashSv(d8, hBitsS, mls);
             u32 const tl = active ? hashLong[hl] : 0, ts = active ? hashSmall[hs] : 0;
+            u32 const myTagL = tag8(d8), myTagS = tag4((u32)d8);
             // lane 0 sits at ip: fold the immediate-repcode test into this batch (its load overlaps the table loads)
             bool const rep2Hit = rep2Pending && lane == 0 && off2 > 0 && (load32(src + p - (int)off2) == (u32)d8);
             u32 const mL = w.match_any(active ? hl : (0x80000000u | lane));
@@ -320,13 +330,17 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             u32 const lowL = mL & below, lowS = mS & below;
             int const pL = w.shfl(p, lowL ? (int)highbit32(lowL) : (int)lane);
             int const pS = w.shfl(p, lowS ? (int)highbit32(lowS) : (int)lane);
-            idxl = lowL ? (u32)pL + 2 : tl;
-            idxs = lowS ? (u32)pS + 2 : ts;
+            idxl = lowL ? (u32)pL + 2 : (tl & CELL_IDX_MASK);
+            idxs = lowS ? (u32)pS + 2 : (ts & CELL_IDX_MASK);
+            // candidates forwarded from an earlier lane are a few bytes away (cached); table candidates are only
+            // worth a fetch when their fingerprint matches
+            plausL = idxl >= 2 && (lowL || (tl >> 18) == myTagL);
+            bool const plausS = idxs >= 2 && (lowS || (ts >> 18) == myTagS);
             kind = 0;
             if (active) {
                 bool const repOk = (off1 > 0) && (load32(src + p + 1 - (int)off1) == (u32)(d8 >> 8));
-                bool const longOk = (idxl >= 2) && (load64(src + (idxl - 2)) == d8);
-                bool const shortOk = (idxs >= 2) && (load32(src + (idxs - 2)) == (u32)d8);
+                bool const longOk = plausL && (load64(src + (idxl - 2)) == d8);
+                bool const shortOk = plausS && (load32(src + (idxs - 2)) == (u32)d8);
                 kind = rep2Hit ? 4 : repOk ? 1 : longOk ? 2 : shortOk ? 3 : 0;
             }
             u32 const hm = w.ballot(kind != 0);
@@ -335,8 +349,8 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             int const last = ev >= 0 ? ev : (int)nActive - 1;
             if (active && (int)lane <= last) {
                 u32 const later = ((last >= 31) ? 0xFFFFFFFFu : ((2u << last) - 1)) & ~((2u << lane) - 1);
-                if (!(mL & later)) hashLong[hl] = (u32)p + 2;
-                if (!(mS & later)) hashSmall[hs] = (u32)p + 2;
+                if (!(mL & later)) hashLong[hl] = cell((u32)p + 2, myTagL);
+                if (!(mS & later)) hashSmall[hs] = cell((u32)p + 2, myTagS);
             }
             w.sync();
             rep2Pending = false;
@@ -367,9 +381,10 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
         u32 const ste = w.shfl(st, ev), idxle = w.shfl(idxl, ev), idxse = w.shfl(idxs, ev);
         bool const nextInBatch = (ev + 1 < (int)nActive);
         int const nl = nextInBatch ? ev + 1 : ev;
-        u32 hl1 = w.shfl(hl, nl), idxl1 = w.shfl(idxl, nl); u64 d81 = w.shfl(d8, nl);
+        u32 hl1 = w.shfl(hl, nl), idxl1 = w.shfl(idxl, nl); u64 d81 = w.shfl(d8, nl); bool plaus1 = w.shfl((u32)plausL, nl) != 0;
         if (kinde != 1 && !nextInBatch) {   // position ip1 was not part of the batch: read it now (tables are committed)
-            d81 = load64(src + p1e); hl1 = hash8v(d81, hBitsL); idxl1 = hashLong[hl1];
+            d81 = load64(src + p1e); hl1 = hash8v(d81, hBitsL);
+            u32 const c1 = hashLong[hl1]; idxl1 = c1 & CELL_IDX_MASK; plaus1 = idxl1 >= 2 && (c1 >> 18) == tag8(d81);
         }
         u32 mLength, offset = 0; int mpos;
         if (kinde == 1) {
@@ -387,7 +402,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
                 mpos = (int)idxse - 2;
                 mLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)mpos + 4) + 4;
                 offset = (u32)(ip - mpos);
-                if ((idxl1 > 2) && (load64(src + (idxl1 - 2)) == d81)) {
+                if ((idxl1 > 2) && plaus1 && (load64(src + (idxl1 - 2)) == d81)) {
                     int const m1 = (int)idxl1 - 2;
                     u32 const l1len = wcount(w, src, (u32)n, (u32)p1e + 8, (u32)m1 + 8) + 8;
                     if (l1len > mLength) { ip = p1e; mLength = l1len; offset = (u32)(ip - m1); mpos = m1; }
@@ -398,7 +413,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
                 ip -= (int)back; mLength += back; }
             off2 = off1; off1 = offset;
             if (lane == 0) {
-                if (ste < 4) hashLong[hl1] = (u32)p1e + 2;
+                if (ste < 4) hashLong[hl1] = cell((u32)p1e + 2, tag8(d81));
                 W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = offset + 3; W.seqML[nbSeq] = mLength;
             }
             nbSeq++;
@@ -408,10 +423,10 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             if (lane == 0) {   // complementary insertions, in the reference's order (:297-305)
                 u32 const A = (u32)pe + 2;
                 u64 const dA = load64(src + A), dB = load64(src + ip - 2), dC = load64(src + ip - 1);
-                hashLong[hash8v(dA, hBitsL)] = A + 2;
-                hashLong[hash8v(dB, hBitsL)] = (u32)ip - 2 + 2;
-                hashSmall[hashSv(dA, hBitsS, mls)] = A + 2;
-                hashSmall[hashSv(dC, hBitsS, mls)] = (u32)ip - 1 + 2;
+                hashLong[hash8v(dA, hBitsL)] = cell(A + 2, tag8(dA));
+                hashLong[hash8v(dB, hBitsL)] = cell((u32)ip - 2 + 2, tag8(dB));
+                hashSmall[hashSv(dA, hBitsS, mls)] = cell(A + 2, tag4((u32)dA));
+                hashSmall[hashSv(dC, hBitsS, mls)] = cell((u32)ip - 1 + 2, tag4((u32)dC));
             }
             rep2Pending = true;
         }

@@ -279,6 +279,17 @@ class ZstdBatchContext(_AutoClose):
     def kernelLaunches(self) -> int:
         return N.lib().zstdb200_kernel_launches(self._live())
 
+    def kernelTimes(self) -> dict:
+        """{kernel: (average ms, launches)} since the previous call (needs setOption("timing", 1))."""
+        buf = C.create_string_buffer(4096)
+        N.lib().zstdb200_kernel_times(self._live(), buf, len(buf))
+        out = {}
+        for part in buf.value.decode().split(";"):
+            if part:
+                name, ms, cnt = part.split(":")
+                out[name] = (float(ms), int(cnt))
+        return out
+
     def setOption(self, name: str, value: int):
         if N.lib().zstdb200_set_option(self._live(), name.encode(), value) != 0:
             raise KeyError(name)
