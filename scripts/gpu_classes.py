@@ -16,15 +16,16 @@ if mode == "sweep":
     d_src = torch.from_numpy(data.reshape(-1)).to(dev)
     d_off = torch.arange(0, (n + 1) * 131072, 131072, dtype=torch.int64, device=dev)
     d_slots = torch.empty(n * stride, dtype=torch.uint8, device=dev); d_sizes = torch.zeros(n, dtype=torch.int64, device=dev)
-    for lanes, wps, pb in ((32, 0, 8), (32, 0, 12), (32, 0, 16), (16, 0, 8)):
+    for lanes, wps, pb, gran in ((32, 0, 8, 64), (32, 0, 8, 32), (32, 0, 12, 32), (32, 0, 16, 32), (32, 0, 16, 64), (32, 0, 12, 64), (32, 0, 6, 64), (32, 0, 4, 64), (32, 0, 8, 128)):
         for _rep in (0,):
+            ctx.setOption("l2_fetch_granularity", gran)
             ctx.setOption("parse_lanes", lanes); ctx.setOption("enc_warps_per_sm", wps); ctx.setOption("skip_entropy", 1); ctx.setOption("parse_blocks_per_sm", pb)
             with torch.cuda.stream(stream):
                 fn = lambda: L.zstdb200_compress_device(ctx.handle, 3, n, d_src.data_ptr(), d_off.data_ptr(), d_slots.data_ptr(), stride, d_sizes.data_ptr(), st)
                 fn(); torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
-            print(f"parse only: lanes={lanes:2d} blocks/SM={pb:2d}: {e0.elapsed_time(e1):8.2f} ms for {n} frames", flush=True)
+            print(f"parse only: lanes={lanes:2d} blocks/SM={pb:2d} l2fetch={gran:3d}: {e0.elapsed_time(e1):8.2f} ms for {n} frames", flush=True)
     sys.exit(0)
 for cls in list(range(8)) + [-1]:
     idx = [cls + 8 * k for k in range(n)] if cls >= 0 else list(range(n))

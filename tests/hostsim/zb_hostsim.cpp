@@ -12,6 +12,12 @@
 extern "C" {
 
 size_t zbh_compress_bound(size_t n) { return zb::compress_bound(n); }
+#ifdef ZB_STATS
+void zbh_parse_stats(unsigned long long* out, int reset) {
+    memcpy(out, &zb::g_parseStats, sizeof zb::g_parseStats);
+    if (reset) memset(&zb::g_parseStats, 0, sizeof zb::g_parseStats);
+}
+#endif
 
 size_t zbh_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level) {
     using namespace zb;

@@ -85,6 +85,15 @@ ZB_HD u32 umax(u32 a, u32 b) { return a > b ? a : b; }
 // misaligned wide loads, and an aligned word that holds at least one valid byte is
 // always inside the same allocation (cudaMalloc / caching allocators round to >=256 B).
 ZB_HD u64 ld_aligned64(const u8* p) { return *reinterpret_cast<const u64*>(p); }
+// Random single-word probes (hash-table cells): cache in L2 only.  Through L1 every miss pulls a whole 128-byte
+// line over the crossbar and out of HBM for 4 useful bytes (measured: 3x the requested sectors, profiles/).
+ZB_HD u32 ld_probe32(const u32* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
 ZB_HD u64 load64(const u8* p) {
     uintptr_t const a = reinterpret_cast<uintptr_t>(p);
     u32 const sh = (u32)(a & 7) * 8;

@@ -91,7 +91,13 @@ ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize,
             for (int t = 0; t < 3; t++) {
                 u32 const nE = 1u << S.fseLog[t];
                 u32* const out = fseOut + (t == 0 ? 0 : t == 1 ? FAST_FSE_OF : FAST_FSE_ML);
-                for (u32 i = (u32)w.lane; i < nE; i += C::W) out[i] = S.fse[t][i];
+                // bits 10..14 of the copy carry the code's extra-bit count, so that stage C learns every bit count of
+                // a sequence from the three state entries alone
+                for (u32 i = (u32)w.lane; i < nE; i += C::W) {
+                    u32 const e = S.fse[t][i], sym = e >> 24;
+                    u32 const extra = t == 0 ? ZB_T.LL_bits[sym] : t == 1 ? sym : ZB_T.ML_bits[sym];
+                    out[i] = e | (extra << 10);
+                }
             }
         }
     } while (0);
@@ -114,39 +120,83 @@ ZB_HDN void dec_huf(DecDesc* d, int k, const u8* blk, const u16* huf, u8* lit) {
 // 2^28-1, which the executor rejects exactly like the originals).
 // `fse` = the frame's three tables (FAST_FSE_ENTRIES u32, in shared memory on the GPU), `ct` = code tables
 // (shared memory copy on the GPU: per-lane indices would serialise in the constant cache).
+// Backward bit reader of one thread.  The serial chain of the sequence stream is state -> entry -> bit counts ->
+// bits -> state; a memory load on that chain costs hundreds of cycles per sequence.  Here the next bits always sit
+// in a 64-bit register window that is topped up 32 bits at a time from a queue of aligned 16-byte loads issued one
+// quad (four to five sequences) ahead of their use.  Bits below the first byte of the stream read as zero and `pos`
+// keeps counting down, exactly like peek_bits (N/common/bitstream.h:344-351 zero-filled container).
+struct BackBits {
+    const u8* A16; u32 startByte; int quad;
+    u32 c0, c1, c2, c3, qn;     // current quad; the next word to hand out is c3
+    u32 p0, p1, p2, p3;         // quad below it, already in flight
+    u64 win; u32 avail; i64 pos;
+
+    ZB_HD void load_quad(int q, u32& a, u32& b, u32& c, u32& d) const {
+        if (q < 0) { a = b = c = d = 0; return; }
+        const u8* const P = A16 + (size_t)q * 16;
+        u64 lo = ld_aligned64(P), hi = ld_aligned64(P + 8);
+        if (q == 0 && startByte) {
+            if (startByte >= 8) { lo = 0; hi &= ~0ull << (8 * (startByte - 8)); } else lo &= ~0ull << (8 * startByte);
+        }
+        a = (u32)lo; b = (u32)(lo >> 32); c = (u32)hi; d = (u32)(hi >> 32);
+    }
+    ZB_HD u32 next_word() {
+        if (qn == 0) { c0 = p0; c1 = p1; c2 = p2; c3 = p3; qn = 4; load_quad(quad, p0, p1, p2, p3); quad--; }
+        u32 const v = c3; c3 = c2; c2 = c1; c1 = c0; qn--;
+        return v;
+    }
+    // `bits` = number of stream bits below the end mark, stream bytes at ip
+    ZB_HD void init(const u8* ip, i64 bits) {
+        uintptr_t const a = reinterpret_cast<uintptr_t>(ip);
+        A16 = reinterpret_cast<const u8*>(a & ~(uintptr_t)15); startByte = (u32)(a & 15);
+        pos = bits; win = 0; avail = 0; qn = 0; c0 = c1 = c2 = c3 = 0;
+        i64 const gpos = bits + 8 * (i64)startByte;
+        if (gpos <= 0) { quad = -1; p0 = p1 = p2 = p3 = 0; return; }
+        int const k0 = (int)((gpos - 1) >> 5); u32 const r = (u32)(gpos - 32 * (i64)k0);     // 1..32 valid bits in the top word
+        int const Q0 = k0 >> 2; u32 const j0 = (u32)k0 & 3;
+        load_quad(Q0, c0, c1, c2, c3);
+        for (u32 j = 3; j > j0; j--) { c3 = c2; c2 = c1; c1 = c0; }
+        qn = j0 + 1;
+        load_quad(Q0 - 1, p0, p1, p2, p3); quad = Q0 - 2;
+        u32 const wd = next_word();
+        win = (u64)wd << (64 - r); avail = r;
+    }
+    // next n bits (0..32) as a number
+    ZB_HD u32 take(u32 n) {
+        if (avail < n) { u32 const wd = next_word(); win |= (u64)wd << (32 - avail); avail += 32; }
+        u32 const v = (u32)((win >> 1) >> (63 - n));
+        win <<= n; avail -= n; pos -= (i64)n;
+        return v;
+    }
+};
+
 ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables* ct, u64* seqOut) {
     if (d->mode != 1 || d->stA1 || d->stA2 || d->nbSeq == 0) return;
     const u8* const ip = blk + d->seqOff; size_t const left = d->seqLen;
     if (left < 1 || ip[left - 1] == 0) { d->stC = E_corruption_detected; return; }
     const u32* const tLL = fse; const u32* const tOF = fse + FAST_FSE_OF; const u32* const tML = fse + FAST_FSE_ML;
-    i64 pos = (i64)(left - 1) * 8 + highbit32(ip[left - 1]);
+    BackBits B;
+    B.init(ip, (i64)(left - 1) * 8 + highbit32(ip[left - 1]));
     u32 rep0 = 1, rep1 = 4, rep2 = 8;
-    u32 const logLL = d->logLL, logOF = d->logOF, logML = d->logML;
-    pos -= logLL; u32 sLL = (u32)peek_bits(ip, pos, logLL);
-    pos -= logOF; u32 sOF = (u32)peek_bits(ip, pos, logOF);
-    pos -= logML; u32 sML = (u32)peek_bits(ip, pos, logML);
+    u32 sLL = B.take(d->logLL), sOF = B.take(d->logOF), sML = B.take(d->logML);
     u32 const nbSeq = d->nbSeq;
     for (u32 k = 0; k < nbSeq; k++) {
+        // entry: nextState (bits 0..9) | extra bits of the code (10..14) | nbBits (16..23) | code (24..31)
         u32 const eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
         u32 const llc = eLL >> 24, ofc = eOF >> 24, mlc = eML >> 24;
-        u32 const llBits = ct->LL_bits[llc], mlBits = ct->ML_bits[mlc], ofBits = ofc;
+        u32 const llBits = (eLL >> 10) & 31, mlBits = (eML >> 10) & 31, ofBits = ofc;
         u32 const nLL = (eLL >> 16) & 0xFF, nML = (eML >> 16) & 0xFF, nOF = (eOF >> 16) & 0xFF;
         bool const lastSeq = (k + 1 == nbSeq);
-        u32 const t1 = ofBits + mlBits + llBits, t2 = lastSeq ? 0 : nLL + nML + nOF;
-        // read order below `pos`: offset bits, ML extra, LL extra, then LL / ML / OF state bits
-        u64 x; u32 y;
-        if (t1 + t2 <= 57) { u64 const v = peek_bits(ip, pos - (i64)(t1 + t2), t1 + t2); x = v >> t2; y = (u32)(v & ((1ull << t2) - 1)); }
-        else if (t1 <= 57) { x = peek_bits(ip, pos - (i64)t1, t1); y = (u32)peek_bits(ip, pos - (i64)(t1 + t2), t2); }
-        else { x = (peek_bits(ip, pos - (i64)ofBits, ofBits) << (mlBits + llBits)) | peek_bits(ip, pos - (i64)t1, mlBits + llBits); y = (u32)peek_bits(ip, pos - (i64)(t1 + t2), t2); }
-        pos -= (i64)(t1 + t2);
-        u32 const ofVal = (u32)(x >> (mlBits + llBits));
-        u32 const llBase = ct->LL_base[llc];
-        u32 const matchLength = ct->ML_base[mlc] + (u32)((x >> llBits) & ((1ull << mlBits) - 1));
-        u32 const litLength = llBase + (u32)(x & ((1ull << llBits) - 1));
+        // read order: offset bits, ML extra, LL extra, then LL / ML / OF state bits (ZSTD_decodeSequence :1229-1346)
+        u32 const ofVal = B.take(ofBits);
+        u32 const x = B.take(mlBits + llBits);
+        u32 const y = lastSeq ? 0 : B.take(nLL + nML + nOF);
+        u32 const matchLength = ct->ML_base[mlc] + (x >> llBits);
+        u32 const litLength = ct->LL_base[llc] + (x & ((1u << llBits) - 1));
         u32 offset;
         if (ofBits > 1) { offset = ((1u << ofBits) - 3) + ofVal; rep2 = rep1; rep1 = rep0; rep0 = offset; }
         else {
-            u32 const ll0 = (llBase == 0);          // ZSTD_decodeSequence :1300 tests the base value
+            u32 const ll0 = (llc == 0);          // :1300 tests litLength base == 0, true for code 0 only
             if (ofBits == 0) { offset = ll0 ? rep1 : rep0; rep1 = ll0 ? rep0 : rep1; rep0 = offset; }
             else {
                 u32 const idx = 1 + ll0 + ofVal;
@@ -157,15 +207,15 @@ ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables*
             }
         }
         if (!lastSeq) {
-            sLL = (eLL & 0xFFFF) + (y >> (nML + nOF));
-            sML = (eML & 0xFFFF) + ((y >> nOF) & ((1u << nML) - 1));
-            sOF = (eOF & 0xFFFF) + (y & ((1u << nOF) - 1));
+            sLL = (eLL & 0x3FF) + (y >> (nML + nOF));
+            sML = (eML & 0x3FF) + ((y >> nOF) & ((1u << nML) - 1));
+            sOF = (eOF & 0x3FF) + (y & ((1u << nOF) - 1));
         }
         u64 const l = litLength > 0x3FFFF ? 0x3FFFF : litLength, m = matchLength > 0x3FFFF ? 0x3FFFF : matchLength;
         u64 const o = offset > 0xFFFFFFFu ? 0xFFFFFFFu : offset;
         seqOut[k] = l | (m << 18) | (o << 36);
     }
-    if (pos != 0) d->stC = E_corruption_detected;
+    if (B.pos != 0) d->stC = E_corruption_detected;
 }
 
 // ---------------------------------------------------------------------------------------- stage D

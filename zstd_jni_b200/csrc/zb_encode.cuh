@@ -280,6 +280,14 @@ ZB_HD u32 wcatchup(const C& w, const u8* src, u32 ip, u32 m, u32 maxBack) {
     }
 }
 
+#ifdef ZB_STATS      // host-only instrumentation (tests/hostsim builds): how much of the speculative work is useful
+struct ParseStats { unsigned long long batches, probes, useful, candL, candS, matches, bytes; };
+static ParseStats g_parseStats;
+#define ZB_STAT(x) x
+#else
+#define ZB_STAT(x)
+#endif
+
 template <class C>
 ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t srcSize, u32 hBitsL, u32 hBitsS, u32 mls, u32* lastLL) {
     u32* const hashLong = W.hashLong; u32* const hashSmall = W.hashSmall;
@@ -320,7 +328,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             d8 = active ? load64(src + p) : 0;
             hl = hash8v(d8, hBitsL);
             u32 const hs = hashSv(d8, hBitsS, mls);
-            u32 const tl = active ? hashLong[hl] : 0, ts = active ? hashSmall[hs] : 0;
+            u32 const tl = active ? ld_probe32(hashLong + hl) : 0, ts = active ? ld_probe32(hashSmall + hs) : 0;
             u32 const myTagL = tag8(d8), myTagS = tag4((u32)d8);
             // lane 0 sits at ip: fold the immediate-repcode test into this batch (its load overlaps the table loads)
             bool const rep2Hit = rep2Pending && lane == 0 && off2 > 0 && (load32(src + p - (int)off2) == (u32)d8);
@@ -341,6 +349,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
                 bool const repOk = (off1 > 0) && (load32(src + p + 1 - (int)off1) == (u32)(d8 >> 8));
                 bool const longOk = plausL && (load64(src + (idxl - 2)) == d8);
                 bool const shortOk = plausS && (load32(src + (idxs - 2)) == (u32)d8);
+                ZB_STAT(g_parseStats.probes++; g_parseStats.candL += plausL && !lowL; g_parseStats.candS += plausS && !lowS;)
                 kind = rep2Hit ? 4 : repOk ? 1 : longOk ? 2 : shortOk ? 3 : 0;
             }
             u32 const hm = w.ballot(kind != 0);
@@ -355,6 +364,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             w.sync();
             rep2Pending = false;
             runPos += (ev >= 0) ? (u32)ev + 1 : nActive;
+            ZB_STAT(if (lane == 0) { g_parseStats.batches++; g_parseStats.useful += (ev >= 0) ? (u32)ev + 1 : nActive; })
             if (ev >= 0) break;
             // no match in this batch: continue after its last position
             {   int const L = (int)nActive - 1;
@@ -384,7 +394,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
         u32 hl1 = w.shfl(hl, nl), idxl1 = w.shfl(idxl, nl); u64 d81 = w.shfl(d8, nl); bool plaus1 = w.shfl((u32)plausL, nl) != 0;
         if (kinde != 1 && !nextInBatch) {   // position ip1 was not part of the batch: read it now (tables are committed)
             d81 = load64(src + p1e); hl1 = hash8v(d81, hBitsL);
-            u32 const c1 = hashLong[hl1]; idxl1 = c1 & CELL_IDX_MASK; plaus1 = idxl1 >= 2 && (c1 >> 18) == tag8(d81);
+            u32 const c1 = ld_probe32(hashLong + hl1); idxl1 = c1 & CELL_IDX_MASK; plaus1 = idxl1 >= 2 && (c1 >> 18) == tag8(d81);
         }
         u32 mLength, offset = 0; int mpos;
         if (kinde == 1) {
@@ -433,6 +443,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
         w.sync();
     }
     w.sync();
+    ZB_STAT(if (lane == 0) { g_parseStats.matches += nbSeq; g_parseStats.bytes += (unsigned long long)n; })
     *lastLL = (u32)(n - anchor);
     return nbSeq;
 }
