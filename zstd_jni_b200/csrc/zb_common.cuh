@@ -131,6 +131,54 @@ ZB_HD u64 peek_bits(const u8* p, i64 lo, u32 n) {
     return (w >> sh) & ((n >= 64) ? ~0ull : ((1ull << n) - 1));
 }
 
+// ---- backward bit reader of ONE thread, all in 32-bit registers.
+// The serial chains of the format (Huffman symbol -> bit count -> next symbol; FSE state -> bit counts -> bits ->
+// state) are latency chains: a memory load or a 64-bit shift sequence on them multiplies the cost of every symbol.
+// Here the next bits always sit in the register pair hi:lo (c = bits of hi already consumed, 0..31); reading is one
+// funnel shift, and the word that slides in next (nx) was loaded two words -- hundreds of cycles -- before it is
+// needed, so no load is ever waited for.  Bits below the first byte of the stream read as zero and `pos` keeps
+// counting down, mirroring the reference's zero-filled container (N/common/bitstream.h:344-351).
+ZB_HD u32 fshl32(u32 lo, u32 hi, u32 s) {      // upper 32 bits of (hi:lo) << s, s in 0..31
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+struct BackBits {
+    const u32* W; int wp; u32 firstMask;
+    u32 hi, lo, nx, c;
+    int pos;                          // stream bits not yet consumed (negative once the stream is overrun)
+    ZB_HD u32 fetch(int k) const {
+        u32 v = 0;
+        if (k >= 0) v = W[k];
+        return k == 0 ? v & firstMask : v;
+    }
+    ZB_HD void init(const u8* ip, int bits) {
+        uintptr_t const a = reinterpret_cast<uintptr_t>(ip);
+        W = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+        u32 const sb = (u32)(a & 3);
+        firstMask = 0xFFFFFFFFu << (8 * sb);
+        pos = bits;
+        int const gpos = bits + 8 * (int)sb;
+        if (gpos <= 0) { hi = lo = nx = 0; c = 0; wp = -1; return; }
+        int const k0 = (gpos - 1) >> 5;
+        c = 32u - (u32)(gpos - 32 * k0);          // bits of the top word above the end mark count as consumed
+        hi = fetch(k0); lo = fetch(k0 - 1); nx = fetch(k0 - 2); wp = k0 - 2;
+    }
+    ZB_HD u32 peek32() const { return fshl32(lo, hi, c); }      // the next 32 bits, first bit on top
+    ZB_HD void skip(u32 n) {                                    // n <= 32
+        c += n; pos -= (int)n;
+        if (c >= 32) { c -= 32; hi = lo; lo = nx; wp--; nx = fetch(wp); }
+    }
+    ZB_HD u32 take(u32 n) {                                     // n in 0..32
+        u32 const w32 = peek32();
+        u32 const v = n ? w32 >> (32 - n) : 0;
+        skip(n);
+        return v;
+    }
+};
+
 // ---- per-code extra bits / base values (N/common/zstd_internal.h:119-144; OF: code == bits)
 struct CodeTables {
     u8 LL_bits[MaxLL + 1];

@@ -231,53 +231,28 @@ ZB_HDN bool huf_decode_stream(const u16* table, u32 log, const u8* src, size_t s
     if (srcSize < 1) return false;
     u8 const lastByte = src[srcSize - 1];
     if (lastByte == 0) return false;
-    i64 pos = (i64)(srcSize - 1) * 8 + highbit32(lastByte);     // unread bits; symbols are read from the top down
+    BackBits B;
+    B.init(src, (int)(srcSize - 1) * 8 + (int)highbit32(lastByte));     // symbols are read from the top down
+    u32 const sh = 32 - log;
     size_t i = 0;
-    u32 const mask = (1u << log) - 1;
-    u32 lead = (u32)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);   // symbols before dst is 4-byte aligned
-    // Fast path: W = the 8 stream bytes ending at ceil(pos/8), Wlow = the 8 bytes below.  Four symbols (<= 48 bits) are
-    // decoded from W, then W slides down by whole bytes using Wlow while the next Wlow is already being fetched, so the
-    // only load per round is off the critical path.
-    i64 a = ((pos + 7) >> 3) - 8;
-    if (a >= 8 && n >= 8) {
-        u64 W = load64(src + a), Wlow = load64(src + a - 8);
-        while (i + 4 <= n) {
-            u32 const top = (u32)(8 * (a + 8) - pos);           // bits of W above `pos` (already consumed), 0..7
-            u32 used = 0, pack = 0; int c = 0;
-            int const lim = lead ? (int)lead : 4;
-            for (; c < lim; c++) {
-                u32 const idx = (u32)((W << (top + used)) >> (64 - log)) & mask;
-                u16 const e = table[idx];
-                pack |= (u32)(e & 0xFF) << (8 * c);
-                used += e >> 8;
-            }
-            if (c == 4 && !lead) *reinterpret_cast<u32*>(dst + i) = pack;
-            else for (int k = 0; k < c; k++) dst[i + (size_t)k] = (u8)(pack >> (8 * k));
-            lead = 0; i += (size_t)c; pos -= used;
-            i64 const a2 = ((pos + 7) >> 3) - 8;
-            if (a2 < 8) break;
-            u32 const d = (u32)(a - a2);                        // 0..6 whole bytes
-            if (d) W = (W << (8 * d)) | (Wlow >> (64 - 8 * d));
-            Wlow = load64(src + a2 - 8);
-            a = a2;
-        }
+    // head: single symbols until dst is 4-byte aligned, then four symbols per 32-bit store
+    for (; i < n && ((reinterpret_cast<uintptr_t>(dst) + i) & 3); i++) {
+        u16 const e = table[B.peek32() >> sh];
+        dst[i] = (u8)e; B.skip(e >> 8);
     }
-    // tail / short streams: one bounded window read per round
-    while (i < n) {
-        u64 const win = peek_bits(src, pos - 57, 57);
-        u32 used = 0, pack = 0; int c = 0;
-        int const lim = lead ? (int)lead : 4;
-        for (; c < lim && i + (size_t)c < n; c++) {
-            u32 const idx = (u32)(win >> (57 - used - log)) & mask;
-            u16 const e = table[idx];
-            pack |= (u32)(e & 0xFF) << (8 * c);
-            used += e >> 8;
+    for (; i + 4 <= n; i += 4) {
+        u32 pack = 0;
+        for (int k = 0; k < 4; k++) {
+            u16 const e = table[B.peek32() >> sh];
+            pack |= (u32)(e & 0xFF) << (8 * k); B.skip(e >> 8);
         }
-        if (c == 4 && !lead) *reinterpret_cast<u32*>(dst + i) = pack;
-        else for (int k = 0; k < c; k++) dst[i + (size_t)k] = (u8)(pack >> (8 * k));
-        lead = 0; i += (size_t)c; pos -= used;
+        *reinterpret_cast<u32*>(dst + i) = pack;
     }
-    return pos == 0;
+    for (; i < n; i++) {
+        u16 const e = table[B.peek32() >> sh];
+        dst[i] = (u8)e; B.skip(e >> 8);
+    }
+    return B.pos == 0;
 }
 
 // ------------------------------------------------------- literals section

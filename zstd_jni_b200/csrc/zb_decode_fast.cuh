@@ -120,67 +120,27 @@ ZB_HDN void dec_huf(DecDesc* d, int k, const u8* blk, const u16* huf, u8* lit) {
 // 2^28-1, which the executor rejects exactly like the originals).
 // `fse` = the frame's three tables (FAST_FSE_ENTRIES u32, in shared memory on the GPU), `ct` = code tables
 // (shared memory copy on the GPU: per-lane indices would serialise in the constant cache).
-// Backward bit reader of one thread.  The serial chain of the sequence stream is state -> entry -> bit counts ->
-// bits -> state; a memory load on that chain costs hundreds of cycles per sequence.  Here the next bits always sit
-// in a 64-bit register window that is topped up 32 bits at a time from a queue of aligned 16-byte loads issued one
-// quad (four to five sequences) ahead of their use.  Bits below the first byte of the stream read as zero and `pos`
-// keeps counting down, exactly like peek_bits (N/common/bitstream.h:344-351 zero-filled container).
-struct BackBits {
-    const u8* A16; u32 startByte; int quad;
-    u32 c0, c1, c2, c3, qn;     // current quad; the next word to hand out is c3
-    u32 p0, p1, p2, p3;         // quad below it, already in flight
-    u64 win; u32 avail; i64 pos;
+// The decoder is a small state machine (begin / step / end) so that a kernel can keep every lane of a warp busy:
+// a lane that finishes its frame picks up the next one while the other lanes keep stepping in lockstep.
+struct SeqDecoder {
+    DecDesc* d; const u32* tLL; const u32* tOF; const u32* tML; const CodeTables* ct; u64* seqOut;
+    BackBits B; u32 sLL, sOF, sML, rep0, rep1, rep2, k, nbSeq;
 
-    ZB_HD void load_quad(int q, u32& a, u32& b, u32& c, u32& d) const {
-        if (q < 0) { a = b = c = d = 0; return; }
-        const u8* const P = A16 + (size_t)q * 16;
-        u64 lo = ld_aligned64(P), hi = ld_aligned64(P + 8);
-        if (q == 0 && startByte) {
-            if (startByte >= 8) { lo = 0; hi &= ~0ull << (8 * (startByte - 8)); } else lo &= ~0ull << (8 * startByte);
-        }
-        a = (u32)lo; b = (u32)(lo >> 32); c = (u32)hi; d = (u32)(hi >> 32);
+    // false: nothing to decode for this item (not eligible, earlier error, no sequences, unusable stream)
+    ZB_HD bool begin(DecDesc* d_, const u8* blk, const u32* fse, const CodeTables* ct_, u64* out) {
+        d = d_;
+        if (d->mode != 1 || d->stA1 || d->stA2 || d->nbSeq == 0) return false;
+        const u8* const ip = blk + d->seqOff; size_t const left = d->seqLen;
+        if (left < 1 || ip[left - 1] == 0) { d->stC = E_corruption_detected; return false; }
+        tLL = fse; tOF = fse + FAST_FSE_OF; tML = fse + FAST_FSE_ML; ct = ct_; seqOut = out;
+        B.init(ip, (int)(left - 1) * 8 + (int)highbit32(ip[left - 1]));
+        rep0 = 1; rep1 = 4; rep2 = 8;
+        sLL = B.take(d->logLL); sOF = B.take(d->logOF); sML = B.take(d->logML);
+        k = 0; nbSeq = d->nbSeq;
+        return true;
     }
-    ZB_HD u32 next_word() {
-        if (qn == 0) { c0 = p0; c1 = p1; c2 = p2; c3 = p3; qn = 4; load_quad(quad, p0, p1, p2, p3); quad--; }
-        u32 const v = c3; c3 = c2; c2 = c1; c1 = c0; qn--;
-        return v;
-    }
-    // `bits` = number of stream bits below the end mark, stream bytes at ip
-    ZB_HD void init(const u8* ip, i64 bits) {
-        uintptr_t const a = reinterpret_cast<uintptr_t>(ip);
-        A16 = reinterpret_cast<const u8*>(a & ~(uintptr_t)15); startByte = (u32)(a & 15);
-        pos = bits; win = 0; avail = 0; qn = 0; c0 = c1 = c2 = c3 = 0;
-        i64 const gpos = bits + 8 * (i64)startByte;
-        if (gpos <= 0) { quad = -1; p0 = p1 = p2 = p3 = 0; return; }
-        int const k0 = (int)((gpos - 1) >> 5); u32 const r = (u32)(gpos - 32 * (i64)k0);     // 1..32 valid bits in the top word
-        int const Q0 = k0 >> 2; u32 const j0 = (u32)k0 & 3;
-        load_quad(Q0, c0, c1, c2, c3);
-        for (u32 j = 3; j > j0; j--) { c3 = c2; c2 = c1; c1 = c0; }
-        qn = j0 + 1;
-        load_quad(Q0 - 1, p0, p1, p2, p3); quad = Q0 - 2;
-        u32 const wd = next_word();
-        win = (u64)wd << (64 - r); avail = r;
-    }
-    // next n bits (0..32) as a number
-    ZB_HD u32 take(u32 n) {
-        if (avail < n) { u32 const wd = next_word(); win |= (u64)wd << (32 - avail); avail += 32; }
-        u32 const v = (u32)((win >> 1) >> (63 - n));
-        win <<= n; avail -= n; pos -= (i64)n;
-        return v;
-    }
-};
-
-ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables* ct, u64* seqOut) {
-    if (d->mode != 1 || d->stA1 || d->stA2 || d->nbSeq == 0) return;
-    const u8* const ip = blk + d->seqOff; size_t const left = d->seqLen;
-    if (left < 1 || ip[left - 1] == 0) { d->stC = E_corruption_detected; return; }
-    const u32* const tLL = fse; const u32* const tOF = fse + FAST_FSE_OF; const u32* const tML = fse + FAST_FSE_ML;
-    BackBits B;
-    B.init(ip, (i64)(left - 1) * 8 + highbit32(ip[left - 1]));
-    u32 rep0 = 1, rep1 = 4, rep2 = 8;
-    u32 sLL = B.take(d->logLL), sOF = B.take(d->logOF), sML = B.take(d->logML);
-    u32 const nbSeq = d->nbSeq;
-    for (u32 k = 0; k < nbSeq; k++) {
+    // one sequence; true while more remain
+    ZB_HD bool step() {
         // entry: nextState (bits 0..9) | extra bits of the code (10..14) | nbBits (16..23) | code (24..31)
         u32 const eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
         u32 const llc = eLL >> 24, ofc = eOF >> 24, mlc = eML >> 24;
@@ -214,8 +174,16 @@ ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables*
         u64 const l = litLength > 0x3FFFF ? 0x3FFFF : litLength, m = matchLength > 0x3FFFF ? 0x3FFFF : matchLength;
         u64 const o = offset > 0xFFFFFFFu ? 0xFFFFFFFu : offset;
         seqOut[k] = l | (m << 18) | (o << 36);
+        return ++k < nbSeq;
     }
-    if (B.pos != 0) d->stC = E_corruption_detected;
+    ZB_HD void end() { if (B.pos != 0) d->stC = E_corruption_detected; }
+};
+
+ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables* ct, u64* seqOut) {
+    SeqDecoder D;
+    if (!D.begin(d, blk, fse, ct, seqOut)) return;
+    while (D.step()) {}
+    D.end();
 }
 
 // ---------------------------------------------------------------------------------------- stage D
