@@ -16,7 +16,7 @@ if mode == "sweep":
     d_src = torch.from_numpy(data.reshape(-1)).to(dev)
     d_off = torch.arange(0, (n + 1) * 131072, 131072, dtype=torch.int64, device=dev)
     d_slots = torch.empty(n * stride, dtype=torch.uint8, device=dev); d_sizes = torch.zeros(n, dtype=torch.int64, device=dev)
-    for lanes, wps, pb, gran in ((32, 0, 8, 64), (32, 0, 8, 32), (32, 0, 12, 32), (32, 0, 16, 32), (32, 0, 16, 64), (32, 0, 12, 64), (32, 0, 6, 64), (32, 0, 4, 64), (32, 0, 8, 128)):
+    for lanes, wps, pb, gran in ((32, 0, 8, 64), (32, 0, 10, 64), (32, 0, 8, 32), (32, 0, 10, 32)):
         for _rep in (0,):
             ctx.setOption("l2_fetch_granularity", gran)
             ctx.setOption("parse_lanes", lanes); ctx.setOption("enc_warps_per_sm", wps); ctx.setOption("skip_entropy", 1); ctx.setOption("parse_blocks_per_sm", pb)

@@ -6,7 +6,7 @@ import collections, csv, os, re, subprocess, sys, tempfile
 rep, kname = sys.argv[1], sys.argv[2]; top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "zstd_jni_b200/lib/libzstdb200.so")], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("ZB_LIB", os.path.join(root, "zstd_jni_b200/lib/libzstdb200.so"))], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=tmp, capture_output=True, text=True).stdout
 funcs = {}; cur = None; fil = None; line = None

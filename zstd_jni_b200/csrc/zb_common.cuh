@@ -145,6 +145,33 @@ ZB_HD u32 fshl32(u32 lo, u32 hi, u32 s) {      // upper 32 bits of (hi:lo) << s,
     return s ? (hi << s) | (lo >> (32 - s)) : hi;
 #endif
 }
+ZB_HD u32 fshr32(u32 lo, u32 hi, u32 s) {      // lower 32 bits of (hi:lo) >> s, s in 0..31
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+// Forward copy of n bytes from m to t by ONE thread with the semantics of a byte-by-byte loop (so an overlapping
+// source, t - m < n, replicates its period like ZSTD_execSequence's match copy), but moving aligned 32-bit words
+// whenever the distance allows it: head bytes until t is word aligned, then one aligned store per word fed by two
+// aligned loads and a funnel shift, then the tail.  The aligned loads may touch up to 3 bytes on either side of
+// the source range inside words that also hold requested bytes; callers guarantee those words are mapped.
+ZB_HD void copy_fwd(u8* t, const u8* m, u32 n) {
+    u32 k = 0;
+    if ((uintptr_t)(t - m) >= 4 && n >= 8) {
+        while ((reinterpret_cast<uintptr_t>(t + k) & 3) != 0) { t[k] = m[k]; k++; }
+        u32 const sh = (u32)(reinterpret_cast<uintptr_t>(m + k) & 3) * 8;
+        const u8* a = m + k - (sh >> 3);
+        for (; k + 4 <= n; k += 4, a += 4) {
+            u32 const w0 = *reinterpret_cast<const u32*>(a);
+            u32 const w1 = sh ? *reinterpret_cast<const u32*>(a + 4) : 0;
+            *reinterpret_cast<u32*>(t + k) = fshr32(w0, w1, sh);
+        }
+    }
+    for (; k < n; k++) t[k] = m[k];
+}
+
 struct BackBits {
     const u32* W; int wp; u32 firstMask;
     u32 hi, lo, nx, c;
@@ -165,11 +192,21 @@ struct BackBits {
         int const k0 = (gpos - 1) >> 5;
         c = 32u - (u32)(gpos - 32 * k0);          // bits of the top word above the end mark count as consumed
         hi = fetch(k0); lo = fetch(k0 - 1); nx = fetch(k0 - 2); wp = k0 - 2;
+#if defined(__CUDA_ARCH__)
+        for (int k = k0 - 32; k >= 0 && k >= k0 - 96; k -= 32) asm volatile("prefetch.L1 [%0];" :: "l"(W + k));
+#endif
     }
     ZB_HD u32 peek32() const { return fshl32(lo, hi, c); }      // the next 32 bits, first bit on top
     ZB_HD void skip(u32 n) {                                    // n <= 32
         c += n; pos -= (int)n;
-        if (c >= 32) { c -= 32; hi = lo; lo = nx; wp--; nx = fetch(wp); }
+        if (c >= 32) {
+            c -= 32; hi = lo; lo = nx; wp--; nx = fetch(wp);
+#if defined(__CUDA_ARCH__)
+            // The lanes of a warp read 32 different streams and step in lockstep: one lane's cache miss stalls all of
+            // them, so every 64 bytes the line two ahead (256 B below) is pulled into L1 long before it is needed.
+            if ((wp & 15) == 0 && wp >= 64) asm volatile("prefetch.L1 [%0];" :: "l"(W + (wp - 64)));
+#endif
+        }
     }
     ZB_HD u32 take(u32 n) {                                     // n in 0..32
         u32 const w32 = peek32();

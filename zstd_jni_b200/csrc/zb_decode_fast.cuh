@@ -233,7 +233,7 @@ ZB_HDN size_t dec_exec(const C& w, const DecDesc* dp, const u8* item, const u8* 
         u32 const good = badMask ? ((1u << ctz32(badMask)) - 1) : C::FULL;      // lanes before the first failure
         bool const mine = ((good >> w.lane) & 1) && i < nbSeq;
         // literals: short runs by their own lane, long ones by everybody
-        if (mine && ll && ll <= 32) { for (u32 k = 0; k < ll; k++) dst[o + k] = rle ? rleByte : lit[ls + k]; }
+        if (mine && ll && ll <= 32) { if (rle) { for (u32 k = 0; k < ll; k++) dst[o + k] = rleByte; } else copy_fwd(dst + o, lit + ls, ll); }
         {   u32 big = w.ballot(mine && ll > 32);
             while (big) {
                 int const b = (int)ctz32(big); big &= big - 1;
@@ -247,7 +247,7 @@ ZB_HDN size_t dec_exec(const C& w, const DecDesc* dp, const u8* item, const u8* 
         while (pending) {
             int const f = (int)ctz32(pending);
             u32 const frontier = w.shfl(md, f), fml = w.shfl(ml, f);
-            if (fml > 96) {          // long match at the frontier: all lanes, period trick for overlaps
+            if (fml > 64) {          // long match at the frontier: all lanes, period trick for overlaps
                 u32 const foff = w.shfl(off, f);
                 u8* const t = dst + frontier; const u8* const m = t - foff;
                 if (foff >= fml) { for (u32 k = (u32)w.lane; k < fml; k += C::W) t[k] = m[k]; }
@@ -257,8 +257,8 @@ ZB_HDN size_t dec_exec(const C& w, const DecDesc* dp, const u8* item, const u8* 
                 w.sync();
                 continue;
             }
-            bool const ready = ((pending >> w.lane) & 1) && ((int)w.lane == f || (ml <= 96 && md - off + ml <= frontier));
-            if (ready) { u8* const t = dst + md; const u8* const m = t - off; for (u32 k = 0; k < ml; k++) t[k] = m[k]; }
+            bool const ready = ((pending >> w.lane) & 1) && ((int)w.lane == f || (ml <= 64 && md - off + ml <= frontier));
+            if (ready) copy_fwd(dst + md, dst + md - off, ml);
             pending &= ~w.ballot(ready);
             w.sync();
         }
