@@ -158,8 +158,10 @@ ZB_HD u32 fshr32(u32 lo, u32 hi, u32 s) {      // lower 32 bits of (hi:lo) >> s,
 // aligned loads and a funnel shift, then the tail.  The aligned loads may touch up to 3 bytes on either side of
 // the source range inside words that also hold requested bytes; callers guarantee those words are mapped.
 ZB_HD void copy_fwd(u8* t, const u8* m, u32 n) {
+    uintptr_t const off = (uintptr_t)(t - m);
+    if (off < 8 && n > off) { for (u32 k = 0; k < n; k++) t[k] = m[k]; return; }     // short period: replicate byte by byte
     u32 k = 0;
-    if ((uintptr_t)(t - m) >= 4 && n >= 8) {
+    if (n > 16) {      // long: aligned words
         while ((reinterpret_cast<uintptr_t>(t + k) & 3) != 0) { t[k] = m[k]; k++; }
         u32 const sh = (u32)(reinterpret_cast<uintptr_t>(m + k) & 3) * 8;
         const u8* a = m + k - (sh >> 3);
@@ -169,18 +171,25 @@ ZB_HD void copy_fwd(u8* t, const u8* m, u32 n) {
             *reinterpret_cast<u32*>(t + k) = fshr32(w0, w1, sh);
         }
     }
-    for (; k < n; k++) t[k] = m[k];
+    // short (and the tail of long): eight source bytes per step come from one unaligned read, the stores are
+    // independent of each other, so there is no load -> store -> load chain
+    for (; k < n; k += 8) {
+        u32 const r = n - k < 8 ? n - k : 8;
+        u64 const v = load64_n(m + k, r);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (u32 j = 0; j < 8; j++) if (j < r) t[k + j] = (u8)(v >> (8 * j));
+    }
 }
 
 struct BackBits {
     const u32* W; int wp; u32 firstMask;
-    u32 hi, lo, nx, c;
+    u32 hi, lo, nx, nmask, c;         // nx is kept as loaded; its mask is applied one step later, when it moves into lo,
+                                      // so that nothing consumes a load result in the step that issued the load
     int pos;                          // stream bits not yet consumed (negative once the stream is overrun)
-    ZB_HD u32 fetch(int k) const {
-        u32 v = 0;
-        if (k >= 0) v = W[k];
-        return k == 0 ? v & firstMask : v;
-    }
+    ZB_HD u32 raw(int k) const { u32 v = 0; if (k >= 0) v = W[k]; return v; }
+    ZB_HD u32 mask_of(int k) const { return k == 0 ? firstMask : 0xFFFFFFFFu; }
     ZB_HD void init(const u8* ip, int bits) {
         uintptr_t const a = reinterpret_cast<uintptr_t>(ip);
         W = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
@@ -188,10 +197,10 @@ struct BackBits {
         firstMask = 0xFFFFFFFFu << (8 * sb);
         pos = bits;
         int const gpos = bits + 8 * (int)sb;
-        if (gpos <= 0) { hi = lo = nx = 0; c = 0; wp = -1; return; }
+        if (gpos <= 0) { hi = lo = nx = 0; nmask = 0; c = 0; wp = -1; return; }
         int const k0 = (gpos - 1) >> 5;
         c = 32u - (u32)(gpos - 32 * k0);          // bits of the top word above the end mark count as consumed
-        hi = fetch(k0); lo = fetch(k0 - 1); nx = fetch(k0 - 2); wp = k0 - 2;
+        hi = raw(k0) & mask_of(k0); lo = raw(k0 - 1) & mask_of(k0 - 1); nx = raw(k0 - 2); nmask = mask_of(k0 - 2); wp = k0 - 2;
 #if defined(__CUDA_ARCH__)
         for (int k = k0 - 32; k >= 0 && k >= k0 - 96; k -= 32) asm volatile("prefetch.L1 [%0];" :: "l"(W + k));
 #endif
@@ -200,7 +209,7 @@ struct BackBits {
     ZB_HD void skip(u32 n) {                                    // n <= 32
         c += n; pos -= (int)n;
         if (c >= 32) {
-            c -= 32; hi = lo; lo = nx; wp--; nx = fetch(wp);
+            c -= 32; hi = lo; lo = nx & nmask; wp--; nx = raw(wp); nmask = mask_of(wp);
 #if defined(__CUDA_ARCH__)
             // The lanes of a warp read 32 different streams and step in lockstep: one lane's cache miss stalls all of
             // them, so every 64 bytes the line two ahead (256 B below) is pulled into L1 long before it is needed.
