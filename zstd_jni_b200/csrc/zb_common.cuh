@@ -87,6 +87,13 @@ ZB_HD u32 umax(u32 a, u32 b) { return a > b ? a : b; }
 ZB_HD u64 ld_aligned64(const u8* p) { return *reinterpret_cast<const u64*>(p); }
 // Random single-word probes (hash-table cells): cache in L2 only.  Through L1 every miss pulls a whole 128-byte
 // line over the crossbar and out of HBM for 4 useful bytes (measured: 3x the requested sectors, profiles/).
+ZB_HD void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
 ZB_HD u32 ld_probe32(const u32* p) {
 #if defined(__CUDA_ARCH__)
     return __ldcg(p);

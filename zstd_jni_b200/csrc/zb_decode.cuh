@@ -227,32 +227,38 @@ ZB_HDN size_t huf_read_table(const C& w, DecShared& S, const u8* src, size_t src
 }
 
 // one backward Huffman stream -> n symbols at dst (HUF_decompress1X1_usingDTable_internal_body :574-595)
+// The symbol -> bit count -> next symbol chain is pure latency, so the loop is built to put as few instructions
+// as possible on it: the unread bits sit left-aligned in a 64-bit register (the table index is a shift of its
+// upper half), two symbols are decoded per refill check, and the two words that will slide in next are already in
+// registers (their loads were issued two refills earlier).  Bits below the first byte read as zero, `pos` counts
+// the unread bits and goes negative on overrun, like BackBits.
 ZB_HDN bool huf_decode_stream(const u16* table, u32 log, const u8* src, size_t srcSize, u8* dst, size_t n) {
     if (srcSize < 1) return false;
     u8 const lastByte = src[srcSize - 1];
     if (lastByte == 0) return false;
-    BackBits B;
-    B.init(src, (int)(srcSize - 1) * 8 + (int)highbit32(lastByte));     // symbols are read from the top down
+    BackBits R;                                       // only used for its word addressing / masking helpers
+    R.init(src, (int)(srcSize - 1) * 8 + (int)highbit32(lastByte));
+    int pos = R.pos;
+    // window: hi:lo of the reader with its consumed bits shifted out; then the two look-ahead words
+    u64 win = (((u64)R.hi << 32) | R.lo) << R.c;
+    int avail = 64 - (int)R.c;
+    u32 n0 = R.nx & R.nmask; int wp = R.wp - 1; u32 n1 = R.raw(wp);
     u32 const sh = 32 - log;
+#define ZB_HUF_REFILL() do { if (avail <= 32) { win |= (u64)n0 << (32 - avail); avail += 32; n0 = n1 & R.mask_of(wp); wp--; n1 = R.raw(wp); } } while (0)
+#define ZB_HUF_SYM(outv) do { u16 const e_ = table[(u32)(win >> 32) >> sh]; u32 const nb_ = e_ >> 8; (outv) = e_ & 0xFF; win <<= nb_; avail -= (int)nb_; pos -= (int)nb_; } while (0)
     size_t i = 0;
     // head: single symbols until dst is 4-byte aligned, then four symbols per 32-bit store
-    for (; i < n && ((reinterpret_cast<uintptr_t>(dst) + i) & 3); i++) {
-        u16 const e = table[B.peek32() >> sh];
-        dst[i] = (u8)e; B.skip(e >> 8);
-    }
+    for (; i < n && ((reinterpret_cast<uintptr_t>(dst) + i) & 3); i++) { u32 s0; ZB_HUF_REFILL(); ZB_HUF_SYM(s0); dst[i] = (u8)s0; }
     for (; i + 4 <= n; i += 4) {
-        u32 pack = 0;
-        for (int k = 0; k < 4; k++) {
-            u16 const e = table[B.peek32() >> sh];
-            pack |= (u32)(e & 0xFF) << (8 * k); B.skip(e >> 8);
-        }
-        *reinterpret_cast<u32*>(dst + i) = pack;
+        u32 s0, s1, s2, s3;
+        ZB_HUF_REFILL(); ZB_HUF_SYM(s0); ZB_HUF_SYM(s1);          // avail > 32 >= 2 * 11 bits
+        ZB_HUF_REFILL(); ZB_HUF_SYM(s2); ZB_HUF_SYM(s3);
+        *reinterpret_cast<u32*>(dst + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
     }
-    for (; i < n; i++) {
-        u16 const e = table[B.peek32() >> sh];
-        dst[i] = (u8)e; B.skip(e >> 8);
-    }
-    return B.pos == 0;
+    for (; i < n; i++) { u32 s0; ZB_HUF_REFILL(); ZB_HUF_SYM(s0); dst[i] = (u8)s0; }
+#undef ZB_HUF_REFILL
+#undef ZB_HUF_SYM
+    return pos == 0;
 }
 
 // ------------------------------------------------------- literals section
