@@ -38,7 +38,8 @@ struct DecDesc {
     u32 nbSeq, seqOff, seqLen;                   // sequence bitstream inside the block content
     u32 logLL, logOF, logML;
     u32 regen;
-    u32 pad[3];
+    u32 hufLitSize;      // litSize when the literals are Huffman coded, else 0 (sort key of the Huffman stage)
+    u32 pad[2];
 };
 
 // ---------------------------------------------------------------------------------------- stage A
@@ -49,7 +50,7 @@ ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize,
     L.mode = 0; L.stA1 = L.stB = L.stA2 = L.stC = L.stD = 0; L.regen = 0; L.nbSeq = 0; L.litMode = 0; L.litSize = 0; L.nStreams = 0;
     L.blockOff = L.cSize = L.contentSize = L.rawOff = L.rleByte = L.hufLog = L.seqOff = L.seqLen = L.logLL = L.logOF = L.logML = 0;
     for (int k = 0; k < 4; k++) { L.sOff[k] = L.sLen[k] = L.oOff[k] = L.oCnt[k] = 0; }
-    L.pad[0] = L.pad[1] = L.pad[2] = 0;
+    L.pad[0] = L.pad[1] = 0; L.hufLitSize = 0;
     do {
         if (srcSize < 9) break;
         if (load32(src) != MAGIC) break;
@@ -78,6 +79,7 @@ ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize,
         L.litMode = li.mode; L.litSize = li.litSize; L.rawOff = li.rawOff; L.rleByte = li.rleByte; L.nStreams = li.nStreams; L.hufLog = S.hufLog;
         for (int k = 0; k < 4; k++) { L.sOff[k] = li.sOff[k]; L.sLen[k] = li.sLen[k]; L.oOff[k] = li.oOff[k]; L.oCnt[k] = li.oCnt[k]; }
         if (li.mode == 2) {
+            L.hufLitSize = li.litSize;
             u32 const nE = 1u << S.hufLog;
             for (u32 i = (u32)w.lane; i < nE; i += C::W) hufOut[i] = S.huf[i];
         }
