@@ -92,16 +92,25 @@ struct SymTT { int deltaFindState; u32 deltaNbBits; };
 struct FseCT { u32 tableLog; u16 stateTable[512]; SymTT tt[64]; };
 struct EncShared {
     u32 count[256];
-    HNode node[2 * 256 + 2];
-    u16 rankBase[192], rankCurr[192];
-    u8 hufBits[256]; u16 hufCode[256];
-    u8 weights[256];
+    // The Huffman stage of a frame is finished before its sequence tables are built, so the Huffman scratch (tree
+    // nodes, rank tables, code table, weights) and the OF / ML sequence tables share storage: 9.3 KB per warp
+    // instead of 12.4 KB, i.e. 24 instead of 16 resident warps per SM for k_entropy.
+    union {
+        struct {
+            HNode node[2 * 256 + 2];
+            u16 rankBase[192], rankCurr[192];
+            u8 hufBits[256]; u16 hufCode[256];
+            u8 weights[256];
+        };
+        FseCT ctSeq[2];      // OF, ML
+    };
     i16 norm[64];
     u16 cumul[66];
     u8 tableSymbol[512];
-    FseCT ct[3];            // LL, OF, ML (ct[0] is also borrowed for the Huffman-weight table)
+    FseCT ct0;              // LL (also borrowed for the Huffman-weight table)
     u32 streamBits[4];
     u32 tmp[8];
+    ZB_HD FseCT& ctab(u32 t) { return t == 0 ? ct0 : ctSeq[t - 1]; }
 };
 
 // ---- hashing / matching (N/compress/zstd_compress_internal.h:854-945)
@@ -851,8 +860,8 @@ ZB_HDN size_t huf_write_ctable(EncShared& S, u8* dst, size_t cap, u32 maxSV, u32
         {   size_t const e = fse_normalize(norm, tableLog, cnt, wtSize, m, false); if (isErr(e)) { hSize = e; break; } }
         size_t const h = fse_write_ncount(o, ocap, norm, m, tableLog);
         if (isErr(h)) { hSize = h; break; }
-        fse_build_ctable(S.ct[0], norm, m, tableLog, S.cumul, S.tableSymbol);
-        size_t const c = fse_compress_2states(o + h, ocap - h, wt, wtSize, S.ct[0]);
+        fse_build_ctable(S.ctab(0), norm, m, tableLog, S.cumul, S.tableSymbol);
+        size_t const c = fse_compress_2states(o + h, ocap - h, wt, wtSize, S.ctab(0));
         if (c == 0) { hSize = 0; break; }
         hSize = h + c;
     } while (0);
@@ -879,11 +888,23 @@ ZB_HDN size_t huf_encode_stream(const C& w, const EncShared& S, u8* dst, size_t 
     u32 const B = (u32)((n + C::W - 1) / C::W);
     u32 const j0 = (u32)w.lane * B < (u32)n ? (u32)w.lane * B : (u32)n;
     u32 const j1 = j0 + B < (u32)n ? j0 + B : (u32)n;
+    // every lane walks its own slice, so byte loads would be 32 separate sector requests per instruction and eight
+    // of them per sector: read the slice eight symbols at a time instead
     u32 mine = 0;
-    for (u32 j = j0; j < j1; j++) mine += S.hufBits[src[n - 1 - j]];
+    for (u32 j = j0; j < j1;) {
+        u32 const cnt = j1 - j < 8 ? j1 - j : 8;
+        u64 const v = load64_n(src + (n - j - cnt), cnt);
+        for (u32 k = 0; k < cnt; k++) mine += S.hufBits[(u8)(v >> (8 * (cnt - 1 - k)))];
+        j += cnt;
+    }
     u32 const start = w.exscan(mine);
     LaneBits<C> lb; lb.init(dst, start);
-    for (u32 j = j0; j < j1; j++) { u8 const b = src[n - 1 - j]; lb.add(w, S.hufCode[b], S.hufBits[b]); }
+    for (u32 j = j0; j < j1;) {
+        u32 const cnt = j1 - j < 8 ? j1 - j : 8;
+        u64 const v = load64_n(src + (n - j - cnt), cnt);
+        for (u32 k = 0; k < cnt; k++) { u8 const b = (u8)(v >> (8 * (cnt - 1 - k))); lb.add(w, S.hufCode[b], S.hufBits[b]); }
+        j += cnt;
+    }
     if (w.lane == C::W - 1) lb.add(w, 1, 1);
     lb.close(w);
     w.sync();
@@ -1072,12 +1093,12 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
         size_t c = 0;
         if (w.lane == 0) {   // ZSTD_buildCTable, zstd_compress_sequences.c:242-288
             size_t const capLeft = (size_t)(oend - op);
-            if (type == 1) { fse_build_ctable_rle(S.ct[t], max); if (capLeft == 0) c = ERR(E_dstSize_tooSmall); else { op[0] = codes[0]; c = 1; } }
+            if (type == 1) { fse_build_ctable_rle(S.ctab(t), max); if (capLeft == 0) c = ERR(E_dstSize_tooSmall); else { op[0] = codes[0]; c = 1; } }
             else if (type == 0) {
                 const i16* dn = t == 0 ? ZB_T.LL_defaultNorm : t == 1 ? ZB_T.OF_defaultNorm : ZB_T.ML_defaultNorm;
                 u32 const dmax = t == 0 ? MaxLL : t == 1 ? DefaultMaxOff : MaxML;
                 for (u32 s = 0; s <= dmax; s++) S.norm[s] = dn[s];
-                fse_build_ctable(S.ct[t], S.norm, dmax, dlog, S.cumul, S.tableSymbol);
+                fse_build_ctable(S.ctab(t), S.norm, dmax, dlog, S.cumul, S.tableSymbol);
                 c = 0;
             } else {
                 u32 const FSELog = t == 1 ? OffFSELog : LLFSELog;
@@ -1085,7 +1106,7 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
                 if (S.count[codes[nbSeq - 1]] > 1) { S.count[codes[nbSeq - 1]]--; nbSeq_1--; }
                 size_t r = fse_normalize(S.norm, tableLog, S.count, nbSeq_1, max, nbSeq_1 >= 2048);
                 if (!isErr(r)) r = fse_write_ncount(op, capLeft, S.norm, max, tableLog);
-                if (!isErr(r)) fse_build_ctable(S.ct[t], S.norm, max, tableLog, S.cumul, S.tableSymbol);
+                if (!isErr(r)) fse_build_ctable(S.ctab(t), S.norm, max, tableLog, S.cumul, S.tableSymbol);
                 c = r;
             }
         }
@@ -1106,7 +1127,7 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
         u16* const stb = W.stbits;
         for (int t = w.lane; t < 3; t += C::W) {
             const u8* const codes = t == 0 ? llc : t == 1 ? ofc : mlc;
-            const FseCT& ct = S.ct[t];
+            const FseCT& ct = S.ctab(t);
             u16* const out = stb + (size_t)t * MAX_SEQ;
             u32 state = fse_init_state2(ct, codes[nbSeq - 1]);
             for (u32 n = nbSeq - 1; n-- > 0;) {
@@ -1129,7 +1150,7 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
         }
         u32 const start = w.exscan(mine);
         u32 const seqBits = w.bcast(start + mine, C::W - 1);
-        size_t const totalBits = (size_t)seqBits + S.ct[0].tableLog + S.ct[1].tableLog + S.ct[2].tableLog + 1;
+        size_t const totalBits = (size_t)seqBits + S.ctab(0).tableLog + S.ctab(1).tableLog + S.ctab(2).tableLog + 1;
         size_t const capLeft = (size_t)(oend - op);
         if (capLeft <= 8 || (totalBits >> 3) >= capLeft - 8) return ERR(E_dstSize_tooSmall);
         streamSize = (totalBits + 7) >> 3;
@@ -1148,9 +1169,9 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
             lb.add(w, W.seqOF[n] & (obits >= 32 ? 0xFFFFFFFFu : ((1u << obits) - 1)), obits);
         }
         if (w.lane == C::W - 1) {
-            lb.add(w, S.tmp[2] & ((1u << S.ct[2].tableLog) - 1), S.ct[2].tableLog);
-            lb.add(w, S.tmp[1] & ((1u << S.ct[1].tableLog) - 1), S.ct[1].tableLog);
-            lb.add(w, S.tmp[0] & ((1u << S.ct[0].tableLog) - 1), S.ct[0].tableLog);
+            lb.add(w, S.tmp[2] & ((1u << S.ctab(2).tableLog) - 1), S.ctab(2).tableLog);
+            lb.add(w, S.tmp[1] & ((1u << S.ctab(1).tableLog) - 1), S.ctab(1).tableLog);
+            lb.add(w, S.tmp[0] & ((1u << S.ctab(0).tableLog) - 1), S.ctab(0).tableLog);
             lb.add(w, 1, 1);
         }
         lb.close(w);
@@ -1308,7 +1329,7 @@ ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, 
                 u32 const i = base + (u32)w.lane;
                 u32 const ll = i < nbSeq ? W.seqLL[i] : 0, ml = i < nbSeq ? W.seqML[i] : 0;
                 u32 const lpre = w.exscan(ll), spre = w.exscan(ll + ml);
-                if (ll && ll <= 32) { u8* const d = W.lit + litSize + lpre; const u8* const f = src + sp + spre; for (u32 k = 0; k < ll; k++) d[k] = f[k]; }
+                if (ll && ll <= 32) copy_fwd(W.lit + litSize + lpre, src + sp + spre, ll);
                 u32 big = w.ballot(ll > 32);
                 while (big) {
                     int const b = (int)ctz32(big); big &= big - 1;
