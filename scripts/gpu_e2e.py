@@ -13,8 +13,8 @@ h_src = torch.from_numpy(data.reshape(-1)).pin_memory()
 stride = (L.ZSTD_compressBound(CH) + 32 + 63) // 64 * 64
 h_stream = torch.empty(n * stride, dtype=torch.uint8).pin_memory(); h_back = torch.empty(n * CH, dtype=torch.uint8).pin_memory()
 fsz = (C.c_size_t * n)(); tot = C.c_size_t(0); dsz = (C.c_size_t * n)()
-for slices in (1, 2, 4, 1):
-    ctx.setOption("host_slices", slices)
+for slices, dslices in ((2, 2), (2, 3), (2, 4), (2, 6), (3, 4)):
+    ctx.setOption("host_slices", slices); ctx.setOption("host_slices_dec", dslices)
     ts = []
     for rep in range(4):
         t0 = time.perf_counter()
@@ -27,4 +27,4 @@ for slices in (1, 2, 4, 1):
         ts.append((t1 - t0, t2 - t1b))
     assert torch.equal(h_back, h_src)
     c = min(t[0] for t in ts[1:]); d = min(t[1] for t in ts[1:])
-    print(f"slices={slices}: compress {c*1e3:7.1f} ms ({n*CH/c/1e9:5.2f} GB/s)  decompress {d*1e3:7.1f} ms ({n*CH/d/1e9:5.2f} GB/s)  round trip {n*CH/(c+d)/1e9:5.2f} GB/s", flush=True)
+    print(f"slices={slices}/{dslices}: compress {c*1e3:7.1f} ms ({n*CH/c/1e9:5.2f} GB/s)  decompress {d*1e3:7.1f} ms ({n*CH/d/1e9:5.2f} GB/s)  round trip {n*CH/(c+d)/1e9:5.2f} GB/s", flush=True)

@@ -1130,7 +1130,23 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
             const FseCT& ct = S.ctab(t);
             u16* const out = stb + (size_t)t * MAX_SEQ;
             u32 state = fse_init_state2(ct, codes[nbSeq - 1]);
-            for (u32 n = nbSeq - 1; n-- > 0;) {
+            // Only state -> nbBits -> next state is serial.  The codes (global memory) are read four at a time one
+            // group ahead and their transform entries (shared memory) are fetched before the group's chain starts, so
+            // no memory access sits on the chain except the state-table lookup itself.
+            u32 n = nbSeq - 1;                       // sequences n-1 .. 0 remain
+            u32 ahead = n >= 4 ? load32(codes + (n - 4)) : 0;
+            while (n >= 4) {
+                u32 const cw = ahead;
+                if (n >= 8) ahead = load32(codes + (n - 8));
+                SymTT const t3 = ct.tt[cw >> 24], t2 = ct.tt[(cw >> 16) & 0xFF], t1 = ct.tt[(cw >> 8) & 0xFF], t0 = ct.tt[cw & 0xFF];
+                u32 nb;
+                nb = (state + t3.deltaNbBits) >> 16; out[n - 1] = (u16)((state & ((1u << nb) - 1)) | (nb << 12)); state = ct.stateTable[(int)(state >> nb) + t3.deltaFindState];
+                nb = (state + t2.deltaNbBits) >> 16; out[n - 2] = (u16)((state & ((1u << nb) - 1)) | (nb << 12)); state = ct.stateTable[(int)(state >> nb) + t2.deltaFindState];
+                nb = (state + t1.deltaNbBits) >> 16; out[n - 3] = (u16)((state & ((1u << nb) - 1)) | (nb << 12)); state = ct.stateTable[(int)(state >> nb) + t1.deltaFindState];
+                nb = (state + t0.deltaNbBits) >> 16; out[n - 4] = (u16)((state & ((1u << nb) - 1)) | (nb << 12)); state = ct.stateTable[(int)(state >> nb) + t0.deltaFindState];
+                n -= 4;
+            }
+            while (n-- > 0) {
                 SymTT const tt = ct.tt[codes[n]];
                 u32 const nb = (state + tt.deltaNbBits) >> 16;
                 out[n] = (u16)((state & ((1u << nb) - 1)) | (nb << 12));
