@@ -717,14 +717,58 @@ static unsigned ml_code(uint32_t mlBase) {   /* ZSTD_MLcode, :601-613 */
         return t[mlBase - 32]; }
 }
 
-/* ZSTD_selectEncodingType for a first block and strategy < ZSTD_lazy, zstd_compress_sequences.c:156-204,232-234 */
-static unsigned select_encoding(unsigned max, size_t mostFrequent, size_t nbSeq, unsigned defaultNormLog, int defaultAllowed, unsigned strategy) {
-    (void)max;
+/* -log2(x/256) * 256, zstd_compress_sequences.c:21-44 */
+static unsigned const k_invProbLog256[256] = {
+    0,    2048, 1792, 1642, 1536, 1453, 1386, 1329, 1280, 1236, 1197, 1162, 1130, 1100, 1073, 1047, 1024, 1001, 980,  960,  941,  923,  906,  889,
+    874,  859,  844,  830,  817,  804,  791,  779,  768,  756,  745,  734,  724,  714,  704,  694,  685,  676,  667,  658,  650,  642,  633,  626,
+    618,  610,  603,  595,  588,  581,  574,  567,  561,  554,  548,  542,  535,  529,  523,  517,  512,  506,  500,  495,  489,  484,  478,  473,
+    468,  463,  458,  453,  448,  443,  438,  434,  429,  424,  420,  415,  411,  407,  402,  398,  394,  390,  386,  382,  377,  373,  370,  366,
+    362,  358,  354,  350,  347,  343,  339,  336,  332,  329,  325,  322,  318,  315,  311,  308,  305,  302,  298,  295,  292,  289,  286,  282,
+    279,  276,  273,  270,  267,  264,  261,  258,  256,  253,  250,  247,  244,  241,  239,  236,  233,  230,  228,  225,  222,  220,  217,  215,
+    212,  209,  207,  204,  202,  199,  197,  194,  192,  190,  187,  185,  182,  180,  178,  175,  173,  171,  168,  166,  164,  162,  159,  157,
+    155,  153,  151,  149,  146,  144,  142,  140,  138,  136,  134,  132,  130,  128,  126,  123,  121,  119,  117,  115,  114,  112,  110,  108,
+    106,  104,  102,  100,  98,   96,   94,   93,   91,   89,   87,   85,   83,   82,   80,   78,   76,   74,   73,   71,   69,   67,   66,   64,
+    62,   61,   59,   57,   55,   54,   52,   50,   49,   47,   46,   44,   42,   41,   39,   37,   36,   34,   33,   31,   30,   28,   26,   25,
+    23,   22,   20,   19,   17,   16,   14,   13,   11,   10,   8,    7,    5,    4,    2,    1 };
+static size_t fse_normalizeCount(int16_t* norm, unsigned tableLog, const unsigned* count, size_t total, unsigned maxSV, unsigned useLowProbCount);
+static size_t fse_writeNCount(uint8_t* dst, size_t cap, const int16_t* norm, unsigned maxSV, unsigned tableLog);
+static unsigned fse_optimalTableLog(unsigned maxTableLog, size_t srcSize, unsigned maxSV, unsigned minus);
+
+/* ZSTD_selectEncodingType for a first block (no repeat mode), zstd_compress_sequences.c:156-234:
+ * heuristics for strategy < lazy, estimated bit costs (:205-231 with ZSTD_crossEntropyCost :140-154,
+ * ZSTD_NCountCost :71-79, ZSTD_entropyCost :85-99) from lazy on */
+static unsigned select_encoding(const unsigned* count, unsigned max, size_t mostFrequent, size_t nbSeq, unsigned FSELog,
+                                const int16_t* defaultNorm, unsigned defaultNormLog, int defaultAllowed, unsigned strategy) {
     if (mostFrequent == nbSeq) return (defaultAllowed && nbSeq <= 2) ? 0 : 1;
-    if (defaultAllowed) {
-        size_t const mult = 10 - strategy;
-        size_t const dynamicFse_nbSeq_min = (((size_t)1 << defaultNormLog) * mult) >> 3;
-        if ((nbSeq < dynamicFse_nbSeq_min) || (mostFrequent < (nbSeq >> (defaultNormLog - 1)))) return 0;
+    if (strategy < ZSO_lazy) {
+        if (defaultAllowed) {
+            size_t const mult = 10 - strategy;
+            size_t const dynamicFse_nbSeq_min = (((size_t)1 << defaultNormLog) * mult) >> 3;
+            if ((nbSeq < dynamicFse_nbSeq_min) || (mostFrequent < (nbSeq >> (defaultNormLog - 1)))) return 0;
+        }
+    } else {
+        size_t basicCost = (size_t)-1, compressedCost; unsigned s;
+        if (defaultAllowed) {
+            unsigned const shift = 8 - defaultNormLog; size_t cost = 0;
+            for (s = 0; s <= max; ++s) {
+                unsigned const normAcc = (defaultNorm[s] != -1) ? (unsigned)defaultNorm[s] : 1;
+                cost += count[s] * k_invProbLog256[normAcc << shift];
+            }
+            basicCost = cost >> 8;
+        }
+        {   uint8_t wksp[512]; int16_t norm[64]; size_t NCountCost;
+            unsigned const tableLog = fse_optimalTableLog(FSELog, nbSeq, max, 2);
+            size_t const r = fse_normalizeCount(norm, tableLog, count, nbSeq, max, nbSeq >= 2048);
+            NCountCost = zso_isError(r) ? r : fse_writeNCount(wksp, sizeof(wksp), norm, max, tableLog);
+            {   unsigned cost = 0;
+                for (s = 0; s <= max; ++s) {
+                    unsigned norm256 = (unsigned)((256 * count[s]) / nbSeq);
+                    if (count[s] != 0 && norm256 == 0) norm256 = 1;
+                    cost += count[s] * k_invProbLog256[norm256];
+                }
+                compressedCost = (NCountCost << 3) + (cost >> 8); }
+        }
+        if (basicCost <= compressedCost) return 0;      /* repeatCost is an error value in a first block */
     }
     return 2;
 }
@@ -770,19 +814,19 @@ static size_t entropy_compress(uint8_t* dst, size_t cap, const zso_seqStore* ss,
         } }
     {   uint8_t* const seqHead = op++; unsigned count[64]; unsigned LLtype, OFtype, MLtype; size_t c;
         {   unsigned max = ZSO_MaxLL; size_t const mf = hist(count, &max, llc, nbSeq);
-            LLtype = select_encoding(max, mf, nbSeq, 6, 1, strategy);
+            LLtype = select_encoding(count, max, mf, nbSeq, ZSO_LLFSELog, zso_LL_defaultNorm, 6, 1, strategy);
             c = build_ctable(op, (size_t)(oend - op), &ctLL, ZSO_LLFSELog, LLtype, count, max, llc, nbSeq, zso_LL_defaultNorm, 6, ZSO_MaxLL);
             if (zso_isError(c)) { result = c; goto done; }
             if (LLtype == 2) lastCountSize = c;
             op += c; }
         {   unsigned max = ZSO_MaxOff; size_t const mf = hist(count, &max, ofc, nbSeq);
-            OFtype = select_encoding(max, mf, nbSeq, 5, max <= ZSO_DefaultMaxOff, strategy);
+            OFtype = select_encoding(count, max, mf, nbSeq, ZSO_OffFSELog, zso_OF_defaultNorm, 5, max <= ZSO_DefaultMaxOff, strategy);
             c = build_ctable(op, (size_t)(oend - op), &ctOF, ZSO_OffFSELog, OFtype, count, max, ofc, nbSeq, zso_OF_defaultNorm, 5, ZSO_DefaultMaxOff);
             if (zso_isError(c)) { result = c; goto done; }
             if (OFtype == 2) lastCountSize = c;
             op += c; }
         {   unsigned max = ZSO_MaxML; size_t const mf = hist(count, &max, mlc, nbSeq);
-            MLtype = select_encoding(max, mf, nbSeq, 6, 1, strategy);
+            MLtype = select_encoding(count, max, mf, nbSeq, ZSO_MLFSELog, zso_ML_defaultNorm, 6, 1, strategy);
             c = build_ctable(op, (size_t)(oend - op), &ctML, ZSO_MLFSELog, MLtype, count, max, mlc, nbSeq, zso_ML_defaultNorm, 6, ZSO_MaxML);
             if (zso_isError(c)) { result = c; goto done; }
             if (MLtype == 2) lastCountSize = c;
@@ -822,11 +866,19 @@ done:
 size_t zso_block_fast(zso_seqStore* ss, uint32_t rep[3], const uint8_t* src, size_t srcSize,
                       uint32_t* hashTable, unsigned hlog, unsigned mls, unsigned targetLength);
 
+/* greedy / lazy / lazy2 with the row-based match finder live in zso_lazy.c (levels 5..10, srcSize > 16 KB) */
+size_t zso_block_lazy_row(void* ss, uint32_t rep[3], const uint8_t* src, size_t srcSize,
+                          uint32_t* hashTable, uint8_t* tagTable, unsigned hashLog, unsigned searchLog, unsigned minMatch, unsigned depth);
+
 /* ---------------------------------------------------------------- frame */
 size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t srcSize, int level) {
     uint8_t* const dst = (uint8_t*)dstv; const uint8_t* const src = (const uint8_t*)srcv; zso_cparams cp; size_t pos = 0;
     if (zso_getCParams(&cp, level, srcSize)) return ZSO_ERROR(parameter_unsupported);
-    if (cp.strategy != ZSO_dfast && cp.strategy != ZSO_fast) return ZSO_ERROR(parameter_unsupported);
+    {   /* supported block compressors: fast, dfast, and greedy/lazy/lazy2 when the row match finder is the one the
+         * reference selects (ZSTD_resolveRowMatchFinderMode, zstd_compress.c:238-245: windowLog > 14); the hash-chain
+         * and binary-tree finders are not restated */
+        int const rowLazy = cp.strategy >= ZSO_greedy && cp.strategy <= ZSO_lazy2 && cp.windowLog > 14;
+        if (cp.strategy != ZSO_dfast && cp.strategy != ZSO_fast && !rowLazy) return ZSO_ERROR(parameter_unsupported); }
     if (dstCapacity < 18) return ZSO_ERROR(dstSize_tooSmall);   /* ZSTD_FRAMEHEADERSIZE_MAX :4716 */
     /* ZSTD_writeFrameHeader :4695-4743 : contentSizeFlag=1, no checksum, no dictID; windowSize >= srcSize => singleSegment */
     {   uint32_t const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256);
@@ -850,7 +902,13 @@ size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t src
             ss.seq = (zso_seq*)malloc(sizeof(zso_seq) * (srcSize / 3 + 1)); ss.nbSeq = 0;
             ss.lit = (uint8_t*)malloc(srcSize + 8); ss.litSize = 0;
             if (!hashLong || !hashSmall || !ss.seq || !ss.lit) { free(hashLong); free(hashSmall); free(ss.seq); free(ss.lit); return ZSO_ERROR(GENERIC); }
-            if (cp.strategy == ZSO_dfast) lastLL = block_dfast(&ss, rep, src, srcSize, hashLong, cp.hashLog, hashSmall, cp.chainLog, cp.minMatch);
+            if (cp.strategy >= ZSO_greedy) {
+                uint8_t* const tagTable = (uint8_t*)calloc((size_t)1 << cp.hashLog, 1);
+                if (!tagTable) { free(hashLong); free(hashSmall); free(ss.seq); free(ss.lit); return ZSO_ERROR(GENERIC); }
+                lastLL = zso_block_lazy_row(&ss, rep, src, srcSize, hashLong, tagTable, cp.hashLog, cp.searchLog, cp.minMatch, cp.strategy - ZSO_greedy);
+                free(tagTable);
+            }
+            else if (cp.strategy == ZSO_dfast) lastLL = block_dfast(&ss, rep, src, srcSize, hashLong, cp.hashLog, hashSmall, cp.chainLog, cp.minMatch);
             else lastLL = zso_block_fast(&ss, rep, src, srcSize, hashLong, cp.hashLog, cp.minMatch, cp.targetLength);
             memcpy(ss.lit + ss.litSize, src + srcSize - lastLL, lastLL); ss.litSize += lastLL;   /* ZSTD_storeLastLiterals */
             /* ZSTD_literalsCompressionIsDisabled (zstd_compress_internal.h:685-700): "auto" disables

@@ -1,0 +1,235 @@
+/* zso_lazy.c -- TEST INFRASTRUCTURE (oracle), not product code.
+ *
+ * Plain-C restatement of the greedy / lazy / lazy2 block compressors with the row-based match finder, as libzstd
+ * 1.5.7 runs them for a fresh frame without dictionary (levels 5..10 for 16 KB < srcSize <= 128 KB):
+ *   ZSTD_compressBlock_lazy_generic      N/compress/zstd_lazy.c:1516-1779  (searchMethod = search_rowHash, noDict)
+ *   ZSTD_RowFindBestMatch                N/compress/zstd_lazy.c:1141-1360
+ *   ZSTD_row_update_internal(+Impl)      :885-943,  ZSTD_row_fillHashCache :837-857, ZSTD_row_nextCachedHash :865-878
+ *   ZSTD_row_nextIndex :798-803, ZSTD_row_getMatchMask :1061-1121 (any of its SIMD/SWAR variants: same mask)
+ * Index convention as in the other parsers: index = position + 2, zeroed cells are "nothing".
+ * The hash salt is 0: the salt is XORed before the shift, so it only permutes rows and tags and the emitted
+ * sequences do not depend on it; tag rows start zeroed like a fresh context.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "zso_common.h"
+
+typedef struct { uint32_t litLength, offBase, matchLength; } zso_seq;
+typedef struct { zso_seq* seq; size_t nbSeq; uint8_t* lit; size_t litSize; } zso_seqStore;
+
+#define ROW_TAG_BITS 8
+#define ROW_CACHE 8
+#define K_SEARCH_STRENGTH 8
+#define K_LAZY_SKIPPING_STEP 8
+
+typedef struct {
+    uint32_t* hashTable; uint8_t* tagTable;
+    uint32_t hashCache[ROW_CACHE];
+    uint32_t rowHashLog, rowLog, searchLog, mls;
+    uint32_t nextToUpdate; int lazySkipping;
+    const uint8_t* base;
+} row_state;
+
+static void store_seq(zso_seqStore* ss, const uint8_t* literals, size_t litLength, uint32_t offBase, size_t matchLength) {
+    memcpy(ss->lit + ss->litSize, literals, litLength); ss->litSize += litLength;
+    ss->seq[ss->nbSeq].litLength = (uint32_t)litLength; ss->seq[ss->nbSeq].offBase = offBase; ss->seq[ss->nbSeq].matchLength = (uint32_t)matchLength;
+    ss->nbSeq++;
+}
+static size_t count_match(const uint8_t* in, const uint8_t* match, const uint8_t* end) {
+    const uint8_t* const s = in;
+    while (in + 8 <= end) { uint64_t const d = zso_rd64(in) ^ zso_rd64(match); if (d) return (size_t)(in - s) + ((unsigned)__builtin_ctzll(d) >> 3); in += 8; match += 8; }
+    while (in < end && *in == *match) { in++; match++; }
+    return (size_t)(in - s);
+}
+/* ZSTD_hashPtrSalted with salt 0, zstd_compress_internal.h:898-962 */
+static uint32_t row_hash(const uint8_t* p, uint32_t hBits, uint32_t mls) {
+    switch (mls) {
+    default:
+    case 4: return (zso_rd32(p) * 2654435761U) >> (32 - hBits);
+    case 5: return (uint32_t)(((zso_rd64(p) << 24) * 889523592379ULL) >> (64 - hBits));
+    case 6: return (uint32_t)(((zso_rd64(p) << 16) * 227718039650203ULL) >> (64 - hBits));
+    }
+}
+static uint32_t row_next_index(uint8_t* tagRow, uint32_t rowMask) {      /* :798-803 */
+    uint32_t next = ((uint32_t)*tagRow - 1) & rowMask;
+    next += (next == 0) ? rowMask : 0;
+    *tagRow = (uint8_t)next;
+    return next;
+}
+static void row_fill_cache(row_state* ms, uint32_t idx, const uint8_t* iLimit) {   /* :837-857 */
+    uint32_t const maxElems = (ms->base + idx) > iLimit ? 0 : (uint32_t)(iLimit - (ms->base + idx) + 1);
+    uint32_t const lim = idx + (ROW_CACHE < maxElems ? ROW_CACHE : maxElems);
+    for (; idx < lim; ++idx) ms->hashCache[idx & (ROW_CACHE - 1)] = row_hash(ms->base + idx, ms->rowHashLog + ROW_TAG_BITS, ms->mls);
+}
+static uint32_t row_next_cached(row_state* ms, uint32_t idx) {        /* :865-878 */
+    uint32_t const newHash = row_hash(ms->base + idx + ROW_CACHE, ms->rowHashLog + ROW_TAG_BITS, ms->mls);
+    uint32_t const hash = ms->hashCache[idx & (ROW_CACHE - 1)];
+    ms->hashCache[idx & (ROW_CACHE - 1)] = newHash;
+    return hash;
+}
+static void row_update_impl(row_state* ms, uint32_t idx, uint32_t end) {   /* :885-908, useCache = 1 */
+    uint32_t const rowMask = (1u << ms->rowLog) - 1;
+    for (; idx < end; ++idx) {
+        uint32_t const hash = row_next_cached(ms, idx);
+        uint32_t const relRow = (hash >> ROW_TAG_BITS) << ms->rowLog;
+        uint8_t* const tagRow = ms->tagTable + relRow;
+        uint32_t const pos = row_next_index(tagRow, rowMask);
+        tagRow[pos] = (uint8_t)hash;
+        ms->hashTable[relRow + pos] = idx;
+    }
+}
+static void row_update(row_state* ms, const uint8_t* ip) {               /* :916-943 */
+    uint32_t idx = ms->nextToUpdate;
+    uint32_t const target = (uint32_t)(ip - ms->base);
+    if (target - idx > 384) {
+        row_update_impl(ms, idx, idx + 96);
+        idx = target - 32;
+        row_fill_cache(ms, idx, ip + 1);
+    }
+    row_update_impl(ms, idx, target);
+    ms->nextToUpdate = target;
+}
+/* ZSTD_RowFindBestMatch :1141-1283 (noDict).  Returns the best length (3 = nothing) and its offBase. */
+static size_t row_find_best(row_state* ms, const uint8_t* ip, const uint8_t* iLimit, size_t* offBasePtr) {
+    uint32_t const curr = (uint32_t)(ip - ms->base);
+    uint32_t const lowLimit = 2;                         /* window.lowLimit of a fresh frame, input <= window */
+    uint32_t const rowEntries = 1u << ms->rowLog, rowMask = rowEntries - 1;
+    uint32_t const cappedSearchLog = ms->searchLog < ms->rowLog ? ms->searchLog : ms->rowLog;
+    uint32_t nbAttempts = 1u << cappedSearchLog;
+    size_t ml = 4 - 1;
+    uint32_t hash;
+    if (!ms->lazySkipping) { row_update(ms, ip); hash = row_next_cached(ms, curr); }
+    else { hash = row_hash(ip, ms->rowHashLog + ROW_TAG_BITS, ms->mls); ms->nextToUpdate = curr; }
+    {   uint32_t const relRow = (hash >> ROW_TAG_BITS) << ms->rowLog;
+        uint32_t const tag = hash & 0xFF;
+        uint32_t* const row = ms->hashTable + relRow;
+        uint8_t* const tagRow = ms->tagTable + relRow;
+        uint32_t const head = *tagRow & rowMask;
+        uint32_t matchBuffer[64]; size_t numMatches = 0, currMatch;
+        uint32_t k;
+        /* the match mask rotated right by head, walked from bit 0: positions head, head+1, ... (mod rowEntries) */
+        for (k = 0; k < rowEntries && nbAttempts > 0; k++) {
+            uint32_t const matchPos = (head + k) & rowMask;
+            uint32_t matchIndex;
+            if (tagRow[matchPos] != (uint8_t)tag) continue;
+            matchIndex = row[matchPos];
+            if (matchPos == 0) continue;
+            if (matchIndex < lowLimit) break;
+            matchBuffer[numMatches++] = matchIndex;
+            --nbAttempts;
+        }
+        {   uint32_t const pos = row_next_index(tagRow, rowMask);
+            tagRow[pos] = (uint8_t)tag;
+            row[pos] = ms->nextToUpdate++;
+        }
+        for (currMatch = 0; currMatch < numMatches; ++currMatch) {
+            const uint8_t* const match = ms->base + matchBuffer[currMatch];
+            size_t currentMl = 0;
+            if (zso_rd32(match + ml - 3) == zso_rd32(ip + ml - 3)) currentMl = count_match(ip, match, iLimit);
+            if (currentMl > ml) {
+                ml = currentMl;
+                *offBasePtr = (size_t)(curr - matchBuffer[currMatch]) + 3;     /* OFFSET_TO_OFFBASE */
+                if (ip + currentMl == iLimit) break;
+            }
+        }
+    }
+    return ml;
+}
+
+/* ZSTD_compressBlock_lazy_generic :1516-1779; depth 0 = greedy, 1 = lazy, 2 = lazy2.  Returns the trailing literal run. */
+size_t zso_block_lazy_row(void* ssv, uint32_t rep[3], const uint8_t* src, size_t srcSize,
+                          uint32_t* hashTable, uint8_t* tagTable, unsigned hashLog, unsigned searchLog, unsigned minMatch, unsigned depth) {
+    zso_seqStore* const ss = (zso_seqStore*)ssv;
+    const uint8_t* const istart = src;
+    const uint8_t* ip = istart;
+    const uint8_t* anchor = istart;
+    const uint8_t* const iend = istart + srcSize;
+    const uint8_t* const ilimit = iend - 8 - ROW_CACHE;
+    const uint8_t* const prefixLowest = src;
+    uint32_t offset_1 = rep[0], offset_2 = rep[1], offsetSaved1 = 0, offsetSaved2 = 0;
+    row_state ms;
+    ms.hashTable = hashTable; ms.tagTable = tagTable; ms.base = src - 2;
+    ms.mls = minMatch < 4 ? 4 : minMatch > 6 ? 6 : minMatch;
+    ms.rowLog = searchLog < 4 ? 4 : searchLog > 6 ? 6 : searchLog;
+    ms.searchLog = searchLog; ms.rowHashLog = hashLog - ms.rowLog;
+    ms.nextToUpdate = 2; ms.lazySkipping = 0;
+
+    ip += 1;                                            /* dictAndPrefixLength == 0 */
+    {   uint32_t const maxRep = (uint32_t)(ip - prefixLowest);
+        if (offset_2 > maxRep) { offsetSaved2 = offset_2; offset_2 = 0; }
+        if (offset_1 > maxRep) { offsetSaved1 = offset_1; offset_1 = 0; }
+    }
+    row_fill_cache(&ms, ms.nextToUpdate, ilimit);
+
+    while (ip < ilimit) {
+        size_t matchLength = 0;
+        size_t offBase = 1;                             /* REPCODE1_TO_OFFBASE */
+        const uint8_t* start = ip + 1;
+        if ((offset_1 > 0) & (zso_rd32(ip + 1 - offset_1) == zso_rd32(ip + 1))) {
+            matchLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
+            if (depth == 0) goto _storeSequence;
+        }
+        {   size_t offbaseFound = 999999999;
+            size_t const ml2 = row_find_best(&ms, ip, iend, &offbaseFound);
+            if (ml2 > matchLength) { matchLength = ml2; start = ip; offBase = offbaseFound; }
+        }
+        if (matchLength < 4) {
+            size_t const step = ((size_t)(ip - anchor) >> K_SEARCH_STRENGTH) + 1;
+            ip += step;
+            ms.lazySkipping = step > K_LAZY_SKIPPING_STEP;
+            continue;
+        }
+        if (depth >= 1)
+        while (ip < ilimit) {
+            ip++;
+            if ((offBase) && ((offset_1 > 0) & (zso_rd32(ip) == zso_rd32(ip - offset_1)))) {
+                size_t const mlRep = count_match(ip + 4, ip + 4 - offset_1, iend) + 4;
+                int const gain2 = (int)(mlRep * 3);
+                int const gain1 = (int)(matchLength * 3 - zso_highbit32((uint32_t)offBase) + 1);
+                if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
+            }
+            {   size_t ofbCandidate = 999999999;
+                size_t const ml2 = row_find_best(&ms, ip, iend, &ofbCandidate);
+                int const gain2 = (int)(ml2 * 4 - zso_highbit32((uint32_t)ofbCandidate));
+                int const gain1 = (int)(matchLength * 4 - zso_highbit32((uint32_t)offBase) + 4);
+                if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; }
+            }
+            if ((depth == 2) && (ip < ilimit)) {
+                ip++;
+                if ((offBase) && ((offset_1 > 0) & (zso_rd32(ip) == zso_rd32(ip - offset_1)))) {
+                    size_t const mlRep = count_match(ip + 4, ip + 4 - offset_1, iend) + 4;
+                    int const gain2 = (int)(mlRep * 4);
+                    int const gain1 = (int)(matchLength * 4 - zso_highbit32((uint32_t)offBase) + 1);
+                    if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
+                }
+                {   size_t ofbCandidate = 999999999;
+                    size_t const ml2 = row_find_best(&ms, ip, iend, &ofbCandidate);
+                    int const gain2 = (int)(ml2 * 4 - zso_highbit32((uint32_t)ofbCandidate));
+                    int const gain1 = (int)(matchLength * 4 - zso_highbit32((uint32_t)offBase) + 7);
+                    if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; }
+                }
+            }
+            break;
+        }
+        if (offBase > 3) {                               /* OFFBASE_IS_OFFSET: catch up */
+            size_t const off = offBase - 3;
+            while (((start > anchor) & (start - off > prefixLowest)) && (start[-1] == (start - off)[-1])) { start--; matchLength++; }
+            offset_2 = offset_1; offset_1 = (uint32_t)off;
+        }
+_storeSequence:
+        store_seq(ss, anchor, (size_t)(start - anchor), (uint32_t)offBase, matchLength);
+        anchor = ip = start + matchLength;
+        if (ms.lazySkipping) { row_fill_cache(&ms, ms.nextToUpdate, ilimit); ms.lazySkipping = 0; }
+        while (((ip <= ilimit) & (offset_2 > 0)) && (zso_rd32(ip) == zso_rd32(ip - offset_2))) {
+            uint32_t tmp;
+            matchLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
+            tmp = offset_2; offset_2 = offset_1; offset_1 = tmp;
+            store_seq(ss, anchor, 0, 1, matchLength);
+            ip += matchLength; anchor = ip;
+        }
+    }
+    offsetSaved2 = ((offsetSaved1 != 0) && (offset_1 != 0)) ? offsetSaved1 : offsetSaved2;
+    rep[0] = offset_1 ? offset_1 : offsetSaved1;
+    rep[1] = offset_2 ? offset_2 : offsetSaved2;
+    return (size_t)(iend - anchor);
+}

@@ -56,6 +56,19 @@ def main():
             fn = f"oneshot_{n:03d}_L{level}.zst"; n += 1
             (HERE / fn).write_bytes(frame)
             man["oneshot"].append({"file": fn, "level": level, "input": spec, "input_sha256": hashlib.sha256(data).hexdigest(), "frame_size": len(frame)})
+    # lazy levels (row match finder, cost-based table selection): the 128 KB inputs and the specials again
+    for spec in specs:
+        data = regenerate_input(spec)
+        if len(data) <= 16384:
+            continue
+        for level in (9, 6, 5):
+            frame = ref_compress(data, level)
+            assert not isinstance(frame, int)
+            if len(frame) > 20000:
+                continue
+            fn = f"oneshot_{n:03d}_L{level}.zst"; n += 1
+            (HERE / fn).write_bytes(frame)
+            man["oneshot"].append({"file": fn, "level": level, "input": spec, "input_sha256": hashlib.sha256(data).hexdigest(), "frame_size": len(frame)})
     # decode-only: the reference's streaming path (multi-block, unknown content size, repeat modes)
     multi = {"kind": "multi", "indices": [1, 9, 5, 17], "size": 450000}
     data = regenerate_input(multi)

@@ -262,6 +262,30 @@ static const CodeTables h_tables = ZB_CODE_TABLES_INIT;
 #define ZB_T (::zb::h_tables)
 #endif
 
+// floor(-log2(x / 256) * 256) for x in [0, 256), 0 for x == 0 (kInverseProbabilityLog256, N/compress/zstd_compress_sequences.c:21-44)
+struct InvProbTable { u16 v[256]; };
+#define ZB_INVPROB_INIT { { \
+    0,    2048, 1792, 1642, 1536, 1453, 1386, 1329, 1280, 1236, 1197, 1162, 1130, 1100, 1073, 1047, 1024, 1001, 980,  960,  941,  923,  906,  889, \
+    874,  859,  844,  830,  817,  804,  791,  779,  768,  756,  745,  734,  724,  714,  704,  694,  685,  676,  667,  658,  650,  642,  633,  626, \
+    618,  610,  603,  595,  588,  581,  574,  567,  561,  554,  548,  542,  535,  529,  523,  517,  512,  506,  500,  495,  489,  484,  478,  473, \
+    468,  463,  458,  453,  448,  443,  438,  434,  429,  424,  420,  415,  411,  407,  402,  398,  394,  390,  386,  382,  377,  373,  370,  366, \
+    362,  358,  354,  350,  347,  343,  339,  336,  332,  329,  325,  322,  318,  315,  311,  308,  305,  302,  298,  295,  292,  289,  286,  282, \
+    279,  276,  273,  270,  267,  264,  261,  258,  256,  253,  250,  247,  244,  241,  239,  236,  233,  230,  228,  225,  222,  220,  217,  215, \
+    212,  209,  207,  204,  202,  199,  197,  194,  192,  190,  187,  185,  182,  180,  178,  175,  173,  171,  168,  166,  164,  162,  159,  157, \
+    155,  153,  151,  149,  146,  144,  142,  140,  138,  136,  134,  132,  130,  128,  126,  123,  121,  119,  117,  115,  114,  112,  110,  108, \
+    106,  104,  102,  100,  98,   96,   94,   93,   91,   89,   87,   85,   83,   82,   80,   78,   76,   74,   73,   71,   69,   67,   66,   64, \
+    62,   61,   59,   57,   55,   54,   52,   50,   49,   47,   46,   44,   42,   41,   39,   37,   36,   34,   33,   31,   30,   28,   26,   25, \
+    23,   22,   20,   19,   17,   16,   14,   13,   11,   10,   8,    7,    5,    4,    2,    1 } }
+#if defined(__CUDACC__)
+static __constant__ InvProbTable c_invprob = ZB_INVPROB_INIT;
+#endif
+static const InvProbTable h_invprob = ZB_INVPROB_INIT;
+#if defined(__CUDA_ARCH__)
+#define ZB_INVPROB (::zb::c_invprob.v)
+#else
+#define ZB_INVPROB (::zb::h_invprob.v)
+#endif
+
 // ---- warp contexts
 #if defined(__CUDACC__)
 // LANES consecutive lanes of a hardware warp acting as one cooperative group (LANES = 32: the whole warp).

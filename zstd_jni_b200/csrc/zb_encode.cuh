@@ -23,7 +23,7 @@
 namespace zb {
 
 struct CParams { u32 windowLog, chainLog, hashLog, searchLog, minMatch, targetLength, strategy; };
-enum : u32 { S_fast = 1, S_dfast = 2 };
+enum : u32 { S_fast = 1, S_dfast = 2, S_greedy = 3, S_lazy = 4, S_lazy2 = 5 };
 
 constexpr u32 MAX_SEQ = (BLOCKSIZE_MAX / 4) + 8;
 constexpr u32 ENC_HASHLOG_MAX = 17;     // largest hashLog / chainLog of the supported rows
@@ -31,15 +31,20 @@ constexpr u32 ENC_HASHLOG_MAX = 17;     // largest hashLog / chainLog of the sup
 // ZSTD_getCParams_internal (:7759-7782) + ZSTD_adjustCParams_internal (:1472-1609) for a known
 // srcSize <= 128 KB, no dictionary.  Returns false when the level selects a parser this build lacks.
 ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize) {
-    // rows 0..4 of the "<=128 KB" and "<=16 KB" tables (clevels.h:78-84,104-109)
-    const CParams t128[5] = { {17,12,12,1,5,1,S_fast}, {17,12,13,1,6,0,S_fast}, {17,13,15,1,5,0,S_fast}, {17,15,16,2,5,0,S_dfast}, {17,17,17,2,4,0,S_dfast} };
+    // rows 0..10 of the "<=128 KB" table and 0..3 of the "<=16 KB" table (clevels.h:78-90,104-109).  Levels 5..10 use
+    // greedy / lazy / lazy2 with the row-based match finder, which the reference selects for windowLog > 14
+    // (ZSTD_resolveRowMatchFinderMode, zstd_compress.c:238-245), i.e. for every srcSize > 16 KB; the hash-chain and
+    // binary-tree finders of the small-input rows are not built.
+    const CParams t128[11] = { {17,12,12,1,5,1,S_fast}, {17,12,13,1,6,0,S_fast}, {17,13,15,1,5,0,S_fast}, {17,15,16,2,5,0,S_dfast}, {17,17,17,2,4,0,S_dfast},
+                               {17,16,17,3,4,2,S_greedy}, {17,16,17,3,4,4,S_lazy}, {17,16,17,3,4,8,S_lazy2}, {17,16,17,4,4,8,S_lazy2}, {17,16,17,5,4,8,S_lazy2},
+                               {17,16,17,6,4,8,S_lazy2} };
     const CParams t16[4] = { {14,12,13,1,5,1,S_fast}, {14,14,15,1,5,0,S_fast}, {14,14,15,1,4,0,S_fast}, {14,14,15,2,4,0,S_dfast} };
     if (srcSize > BLOCKSIZE_MAX) return false;
     int row = level;
     if (level == 0) row = 3;
     if (level < 0) row = 0;
     bool const small = srcSize <= 16 * 1024;
-    if (row > (small ? 3 : 4)) return false;
+    if (row > (small ? 3 : 10)) return false;
     CParams cp = small ? t16[row] : t128[row];
     if (level < 0) { int const l = level < -(1 << 17) ? -(1 << 17) : level; cp.targetLength = (u32)(-l); }
     u32 const tSize = (u32)srcSize;
@@ -1055,6 +1060,32 @@ ZB_HD u32 select_encoding(size_t mostFrequent, size_t nbSeq, u32 defaultNormLog,
     }
     return 2;
 }
+// The same decision for strategy >= lazy (zstd_compress_sequences.c:205-231): estimated bit costs of the predefined
+// table (ZSTD_crossEntropyCost :140-154) against a described one (ZSTD_NCountCost :71-79 + ZSTD_entropyCost :85-99);
+// set_repeat cannot win in a first block.  One lane; S.norm and S.tableSymbol (512 B = FSE_NCOUNTBOUND) are scratch.
+ZB_HDN u32 select_encoding_cost(EncShared& S, u32 max, size_t mostFrequent, size_t nbSeq, u32 FSELog, const i16* defaultNorm, u32 defaultNormLog, bool defaultAllowed) {
+    if (mostFrequent == nbSeq) return (defaultAllowed && nbSeq <= 2) ? 0 : 1;
+    size_t basicCost = (size_t)0 - 1;
+    if (defaultAllowed) {
+        u32 const shift = 8 - defaultNormLog; size_t cost = 0;
+        for (u32 s = 0; s <= max; ++s) {
+            u32 const normAcc = (defaultNorm[s] != -1) ? (u32)defaultNorm[s] : 1;
+            cost += (size_t)S.count[s] * ZB_INVPROB[normAcc << shift];
+        }
+        basicCost = cost >> 8;
+    }
+    u32 const tableLog = fse_optimal_log(FSELog, nbSeq, max, 2);
+    size_t r = fse_normalize(S.norm, tableLog, S.count, nbSeq, max, nbSeq >= 2048);
+    if (!isErr(r)) r = fse_write_ncount(S.tableSymbol, sizeof(S.tableSymbol), S.norm, max, tableLog);
+    u32 cost = 0;
+    for (u32 s = 0; s <= max; ++s) {
+        u32 norm256 = (u32)((256 * (u64)S.count[s]) / nbSeq);
+        if (S.count[s] != 0 && norm256 == 0) norm256 = 1;
+        cost += S.count[s] * ZB_INVPROB[norm256];
+    }
+    size_t const compressedCost = (r << 3) + (cost >> 8);
+    return basicCost <= compressedCost ? 0 : 2;
+}
 
 // ZSTD_entropyCompressSeqStore_internal :2887-3003 on the block body; returns body size, 0 = emit raw block
 template <class C>
@@ -1088,7 +1119,15 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
         u32 const mf = hist_warp(w, S.count, &max, codes, nbSeq);
         bool const defaultAllowed = (t != 1) || (max <= DefaultMaxOff);
         u32 const dlog = t == 1 ? 5 : 6;
-        u32 const type = select_encoding(mf, nbSeq, dlog, defaultAllowed, strategy);
+        u32 type;
+        if (strategy < S_lazy) type = select_encoding(mf, nbSeq, dlog, defaultAllowed, strategy);
+        else {
+            type = 0;
+            if (w.lane == 0) type = select_encoding_cost(S, max, mf, nbSeq, t == 1 ? OffFSELog : t == 0 ? LLFSELog : MLFSELog,
+                                                         t == 0 ? ZB_T.LL_defaultNorm : t == 1 ? ZB_T.OF_defaultNorm : ZB_T.ML_defaultNorm, dlog, defaultAllowed);
+            w.sync();
+            type = w.bcast(type);
+        }
         types[t] = type;
         size_t c = 0;
         if (w.lane == 0) {   // ZSTD_buildCTable, zstd_compress_sequences.c:242-288
@@ -1274,6 +1313,191 @@ ZB_HDN u32 parse_fast(const EncWork& W, const u8* src, size_t srcSize, u32 hlog,
     return nbSeq;
 }
 
+// ZSTD_compressBlock_lazy_generic (N/compress/zstd_lazy.c:1516-1779; depth 0 greedy, 1 lazy, 2 lazy2) with the
+// row-based match finder (ZSTD_RowFindBestMatch :1141-1283, ZSTD_row_update_internal :885-943, hash cache :837-878,
+// ZSTD_row_nextIndex :798-803, match mask :1061-1121), fresh frame, no dictionary.  Serial: call from one lane.
+// hashTable = W.hashLong (1 << hashLog cells), tag rows = the bytes of W.hashSmall; index = position + 2.
+// The hash salt is 0 (it only permutes rows and tags, the sequences do not depend on it).
+struct RowState {
+    u32* hashTable; u8* tagTable; const u8* base;
+    u32 hashCache[8];
+    u32 rowHashLog, rowLog, searchLog, mls, nextToUpdate; bool lazySkipping;
+};
+ZB_HD u32 row_hash(const u8* p, u32 hBits, u32 mls) {
+    switch (mls) {
+    default:
+    case 4: return (load32(p) * 2654435761U) >> (32 - hBits);
+    case 5: return (u32)(((load64(p) << 24) * 889523592379ULL) >> (64 - hBits));
+    case 6: return (u32)(((load64(p) << 16) * 227718039650203ULL) >> (64 - hBits));
+    }
+}
+ZB_HD u32 row_next_index(u8* tagRow, u32 rowMask) {
+    u32 next = ((u32)*tagRow - 1) & rowMask;
+    next += (next == 0) ? rowMask : 0;
+    *tagRow = (u8)next;
+    return next;
+}
+ZB_HD void row_fill_cache(RowState& ms, u32 idx, const u8* iLimit) {
+    u32 const maxElems = (ms.base + idx) > iLimit ? 0 : (u32)(iLimit - (ms.base + idx) + 1);
+    u32 const lim = idx + (8 < maxElems ? 8 : maxElems);
+    for (; idx < lim; ++idx) ms.hashCache[idx & 7] = row_hash(ms.base + idx, ms.rowHashLog + 8, ms.mls);
+}
+ZB_HD u32 row_next_cached(RowState& ms, u32 idx) {
+    u32 const newHash = row_hash(ms.base + idx + 8, ms.rowHashLog + 8, ms.mls);
+    u32 const hash = ms.hashCache[idx & 7];
+    ms.hashCache[idx & 7] = newHash;
+    return hash;
+}
+ZB_HD void row_update_impl(RowState& ms, u32 idx, u32 end) {
+    u32 const rowMask = (1u << ms.rowLog) - 1;
+    for (; idx < end; ++idx) {
+        u32 const hash = row_next_cached(ms, idx);
+        u32 const relRow = (hash >> 8) << ms.rowLog;
+        u8* const tagRow = ms.tagTable + relRow;
+        u32 const pos = row_next_index(tagRow, rowMask);
+        tagRow[pos] = (u8)hash;
+        ms.hashTable[relRow + pos] = idx;
+    }
+}
+ZB_HD void row_update(RowState& ms, const u8* ip) {
+    u32 idx = ms.nextToUpdate;
+    u32 const target = (u32)(ip - ms.base);
+    if (target - idx > 384) {      // kSkipThreshold: only the first 96 and the last 32 positions of a long match are inserted
+        row_update_impl(ms, idx, idx + 96);
+        idx = target - 32;
+        row_fill_cache(ms, idx, ip + 1);
+    }
+    row_update_impl(ms, idx, target);
+    ms.nextToUpdate = target;
+}
+ZB_HDN size_t row_find_best(RowState& ms, const u8* ip, const u8* iLimit, size_t* offBasePtr) {
+    u32 const curr = (u32)(ip - ms.base);
+    u32 const lowLimit = 2;
+    u32 const rowEntries = 1u << ms.rowLog, rowMask = rowEntries - 1;
+    u32 nbAttempts = 1u << (ms.searchLog < ms.rowLog ? ms.searchLog : ms.rowLog);
+    size_t ml = 4 - 1;
+    u32 hash;
+    if (!ms.lazySkipping) { row_update(ms, ip); hash = row_next_cached(ms, curr); }
+    else { hash = row_hash(ip, ms.rowHashLog + 8, ms.mls); ms.nextToUpdate = curr; }
+    u32 const relRow = (hash >> 8) << ms.rowLog;
+    u32 const tag = hash & 0xFF;
+    u32* const row = ms.hashTable + relRow;
+    u8* const tagRow = ms.tagTable + relRow;
+    u32 const head = *tagRow & rowMask;
+    u32 matchBuffer[64]; u32 numMatches = 0;
+    // the reference walks the tag-match mask rotated by head from bit 0: entries head, head+1, ... (mod rowEntries)
+    for (u32 k = 0; k < rowEntries && nbAttempts > 0; k++) {
+        u32 const matchPos = (head + k) & rowMask;
+        if (tagRow[matchPos] != (u8)tag) continue;
+        u32 const matchIndex = row[matchPos];
+        if (matchPos == 0) continue;
+        if (matchIndex < lowLimit) break;
+        matchBuffer[numMatches++] = matchIndex;
+        --nbAttempts;
+    }
+    {   u32 const pos = row_next_index(tagRow, rowMask);
+        tagRow[pos] = (u8)tag;
+        row[pos] = ms.nextToUpdate++; }
+    for (u32 m = 0; m < numMatches; ++m) {
+        const u8* const match = ms.base + matchBuffer[m];
+        size_t currentMl = 0;
+        if (load32(match + ml - 3) == load32(ip + ml - 3)) currentMl = count_match(ip, match, iLimit);
+        if (currentMl > ml) {
+            ml = currentMl;
+            *offBasePtr = (size_t)(curr - matchBuffer[m]) + 3;
+            if (ip + currentMl == iLimit) break;
+        }
+    }
+    return ml;
+}
+ZB_HDN u32 parse_lazy_row(const EncWork& W, const u8* src, size_t srcSize, u32 hashLog, u32 searchLog, u32 minMatch, u32 depth, u32* lastLL) {
+    const u8* const istart = src;
+    const u8* ip = istart;
+    const u8* anchor = istart;
+    const u8* const iend = istart + srcSize;
+    const u8* const ilimit = iend - 8 - 8;
+    const u8* const prefixLowest = src;
+    u32 offset_1 = 1, offset_2 = 4, nbSeq = 0;
+    RowState ms;
+    ms.hashTable = W.hashLong; ms.tagTable = reinterpret_cast<u8*>(W.hashSmall); ms.base = src - 2;
+    ms.mls = minMatch < 4 ? 4 : minMatch > 6 ? 6 : minMatch;
+    ms.rowLog = searchLog < 4 ? 4 : searchLog > 6 ? 6 : searchLog;
+    ms.searchLog = searchLog; ms.rowHashLog = hashLog - ms.rowLog;
+    ms.nextToUpdate = 2; ms.lazySkipping = false;
+    ip += 1;
+    {   u32 const maxRep = (u32)(ip - prefixLowest);
+        if (offset_2 > maxRep) offset_2 = 0;
+        if (offset_1 > maxRep) offset_1 = 0; }
+    row_fill_cache(ms, ms.nextToUpdate, ilimit);
+    while (ip < ilimit) {
+        size_t matchLength = 0;
+        size_t offBase = 1;
+        const u8* start = ip + 1;
+        bool store = false;
+        if ((offset_1 > 0) && (load32(ip + 1 - offset_1) == load32(ip + 1))) {
+            matchLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
+            if (depth == 0) store = true;
+        }
+        if (!store) {
+            {   size_t offbaseFound = 999999999;
+                size_t const ml2 = row_find_best(ms, ip, iend, &offbaseFound);
+                if (ml2 > matchLength) { matchLength = ml2; start = ip; offBase = offbaseFound; } }
+            if (matchLength < 4) {
+                size_t const step = ((size_t)(ip - anchor) >> 8) + 1;      // kSearchStrength
+                ip += step;
+                ms.lazySkipping = step > 8;                                // kLazySkippingStep
+                continue;
+            }
+            if (depth >= 1)
+            while (ip < ilimit) {
+                ip++;
+                if ((offBase) && ((offset_1 > 0) && (load32(ip) == load32(ip - offset_1)))) {
+                    size_t const mlRep = count_match(ip + 4, ip + 4 - offset_1, iend) + 4;
+                    int const gain2 = (int)(mlRep * 3);
+                    int const gain1 = (int)(matchLength * 3 - highbit32((u32)offBase) + 1);
+                    if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
+                }
+                {   size_t ofbCandidate = 999999999;
+                    size_t const ml2 = row_find_best(ms, ip, iend, &ofbCandidate);
+                    int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofbCandidate));
+                    int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 4);
+                    if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; } }
+                if ((depth == 2) && (ip < ilimit)) {
+                    ip++;
+                    if ((offBase) && ((offset_1 > 0) && (load32(ip) == load32(ip - offset_1)))) {
+                        size_t const mlRep = count_match(ip + 4, ip + 4 - offset_1, iend) + 4;
+                        int const gain2 = (int)(mlRep * 4);
+                        int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 1);
+                        if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
+                    }
+                    {   size_t ofbCandidate = 999999999;
+                        size_t const ml2 = row_find_best(ms, ip, iend, &ofbCandidate);
+                        int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofbCandidate));
+                        int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 7);
+                        if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; } }
+                }
+                break;
+            }
+            if (offBase > 3) {   // catch up
+                size_t const off = offBase - 3;
+                while (((start > anchor) && (start - off > prefixLowest)) && (start[-1] == (start - off)[-1])) { start--; matchLength++; }
+                offset_2 = offset_1; offset_1 = (u32)off;
+            }
+        }
+        W.seqLL[nbSeq] = (u32)(start - anchor); W.seqOF[nbSeq] = (u32)offBase; W.seqML[nbSeq] = (u32)matchLength; nbSeq++;
+        anchor = ip = start + matchLength;
+        if (ms.lazySkipping) { row_fill_cache(ms, ms.nextToUpdate, ilimit); ms.lazySkipping = false; }
+        while (((ip <= ilimit) && (offset_2 > 0)) && (load32(ip) == load32(ip - offset_2))) {
+            matchLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
+            u32 const tmp = offset_2; offset_2 = offset_1; offset_1 = tmp;
+            W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = (u32)matchLength; nbSeq++;
+            ip += matchLength; anchor = ip;
+        }
+    }
+    *lastLL = (u32)(iend - anchor);
+    return nbSeq;
+}
+
 // ------------------------------------------------------------------ frame
 // A chunk becomes a frame in two stages that may run in different kernels (and with different group widths):
 //   parse_stage   match finding -> sequences (W.seq*), their count and the trailing literal run
@@ -1288,7 +1512,8 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
     if (!get_cparams(&cp, level, srcSize)) return ERR(E_parameter_unsupported);
     if (srcSize < 7) return 0;
     {   // fresh tables: zero the used part (16-byte stores; the workspace is 16-byte aligned)
-        u32 const nL = (1u << cp.hashLog) / 4, nS = (cp.strategy == S_dfast) ? (1u << cp.chainLog) / 4 : 0;
+        u32 const nL = (1u << cp.hashLog) / 4;
+        u32 const nS = (cp.strategy == S_dfast) ? (1u << cp.chainLog) / 4 : (cp.strategy >= S_greedy) ? (1u << cp.hashLog) / 16 : 0;   // tag bytes
         struct alignas(16) Q { u32 a, b, c, d; };
         Q* const qL = reinterpret_cast<Q*>(W.hashLong); Q* const qS = reinterpret_cast<Q*>(W.hashSmall);
         Q const z = { 0, 0, 0, 0 };
@@ -1300,7 +1525,8 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
         nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
     } else {
         if (w.lane == 0) {
-            if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
+            if (cp.strategy >= S_greedy) nbSeq = parse_lazy_row(W, src, srcSize, cp.hashLog, cp.searchLog, cp.minMatch, cp.strategy - S_greedy, &lastLL);
+            else if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
             else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
         }
         w.sync();
