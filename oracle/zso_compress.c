@@ -866,19 +866,18 @@ done:
 size_t zso_block_fast(zso_seqStore* ss, uint32_t rep[3], const uint8_t* src, size_t srcSize,
                       uint32_t* hashTable, unsigned hlog, unsigned mls, unsigned targetLength);
 
-/* greedy / lazy / lazy2 with the row-based match finder live in zso_lazy.c (levels 5..10, srcSize > 16 KB) */
-size_t zso_block_lazy_row(void* ss, uint32_t rep[3], const uint8_t* src, size_t srcSize,
-                          uint32_t* hashTable, uint8_t* tagTable, unsigned hashLog, unsigned searchLog, unsigned minMatch, unsigned depth);
+/* greedy / lazy / lazy2 live in zso_lazy.c: row-based match finder (levels 5..10, srcSize > 16 KB) or hash chain (levels 4..8, <= 16 KB) */
+size_t zso_block_lazy(void* ss, uint32_t rep[3], const uint8_t* src, size_t srcSize,
+                      uint32_t* hashTable, uint8_t* tagTable, uint32_t* chainTable, unsigned hashLog, unsigned chainLog, unsigned searchLog,
+                      unsigned minMatch, unsigned depth);
 
 /* ---------------------------------------------------------------- frame */
 size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t srcSize, int level) {
     uint8_t* const dst = (uint8_t*)dstv; const uint8_t* const src = (const uint8_t*)srcv; zso_cparams cp; size_t pos = 0;
     if (zso_getCParams(&cp, level, srcSize)) return ZSO_ERROR(parameter_unsupported);
-    {   /* supported block compressors: fast, dfast, and greedy/lazy/lazy2 when the row match finder is the one the
-         * reference selects (ZSTD_resolveRowMatchFinderMode, zstd_compress.c:238-245: windowLog > 14); the hash-chain
-         * and binary-tree finders are not restated */
-        int const rowLazy = cp.strategy >= ZSO_greedy && cp.strategy <= ZSO_lazy2 && cp.windowLog > 14;
-        if (cp.strategy != ZSO_dfast && cp.strategy != ZSO_fast && !rowLazy) return ZSO_ERROR(parameter_unsupported); }
+    /* supported block compressors: fast, dfast, greedy/lazy/lazy2 (row match finder when windowLog > 14,
+     * ZSTD_resolveRowMatchFinderMode zstd_compress.c:238-245, else hash chain); the binary-tree finders are not restated */
+    if (cp.strategy > ZSO_lazy2) return ZSO_ERROR(parameter_unsupported);
     if (dstCapacity < 18) return ZSO_ERROR(dstSize_tooSmall);   /* ZSTD_FRAMEHEADERSIZE_MAX :4716 */
     /* ZSTD_writeFrameHeader :4695-4743 : contentSizeFlag=1, no checksum, no dictID; windowSize >= srcSize => singleSegment */
     {   uint32_t const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256);
@@ -903,9 +902,11 @@ size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t src
             ss.lit = (uint8_t*)malloc(srcSize + 8); ss.litSize = 0;
             if (!hashLong || !hashSmall || !ss.seq || !ss.lit) { free(hashLong); free(hashSmall); free(ss.seq); free(ss.lit); return ZSO_ERROR(GENERIC); }
             if (cp.strategy >= ZSO_greedy) {
-                uint8_t* const tagTable = (uint8_t*)calloc((size_t)1 << cp.hashLog, 1);
-                if (!tagTable) { free(hashLong); free(hashSmall); free(ss.seq); free(ss.lit); return ZSO_ERROR(GENERIC); }
-                lastLL = zso_block_lazy_row(&ss, rep, src, srcSize, hashLong, tagTable, cp.hashLog, cp.searchLog, cp.minMatch, cp.strategy - ZSO_greedy);
+                int const useRow = cp.windowLog > 14;
+                uint8_t* const tagTable = useRow ? (uint8_t*)calloc((size_t)1 << cp.hashLog, 1) : NULL;
+                if (useRow && !tagTable) { free(hashLong); free(hashSmall); free(ss.seq); free(ss.lit); return ZSO_ERROR(GENERIC); }
+                lastLL = zso_block_lazy(&ss, rep, src, srcSize, hashLong, tagTable, hashSmall /* chain table, 1 << chainLog */, cp.hashLog, cp.chainLog,
+                                        cp.searchLog, cp.minMatch, cp.strategy - ZSO_greedy);
                 free(tagTable);
             }
             else if (cp.strategy == ZSO_dfast) lastLL = block_dfast(&ss, rep, src, srcSize, hashLong, cp.hashLog, hashSmall, cp.chainLog, cp.minMatch);

@@ -6,6 +6,8 @@
  *   ZSTD_RowFindBestMatch                N/compress/zstd_lazy.c:1141-1360
  *   ZSTD_row_update_internal(+Impl)      :885-943,  ZSTD_row_fillHashCache :837-857, ZSTD_row_nextCachedHash :865-878
  *   ZSTD_row_nextIndex :798-803, ZSTD_row_getMatchMask :1061-1121 (any of its SIMD/SWAR variants: same mask)
+ * and with the hash-chain finder the reference uses when the window is <= 2^14 (inputs <= 16 KB, levels 4..8):
+ *   ZSTD_HcFindBestMatch :667-733, ZSTD_insertAndFindFirstIndex_internal :632-657
  * Index convention as in the other parsers: index = position + 2, zeroed cells are "nothing".
  * The hash salt is 0: the salt is XORed before the shift, so it only permutes rows and tags and the emitted
  * sequences do not depend on it; tag rows start zeroed like a fresh context.
@@ -28,6 +30,7 @@ typedef struct {
     uint32_t rowHashLog, rowLog, searchLog, mls;
     uint32_t nextToUpdate; int lazySkipping;
     const uint8_t* base;
+    int useRow; uint32_t* chainTable; uint32_t hashLog, chainLog;      /* hash-chain finder */
 } row_state;
 
 static void store_seq(zso_seqStore* ss, const uint8_t* literals, size_t litLength, uint32_t offBase, size_t matchLength) {
@@ -136,15 +139,55 @@ static size_t row_find_best(row_state* ms, const uint8_t* ip, const uint8_t* iLi
     return ml;
 }
 
+/* ZSTD_HcFindBestMatch :667-733 with ZSTD_insertAndFindFirstIndex_internal :632-657 (noDict) */
+static uint32_t hc_hash(const uint8_t* p, uint32_t hBits, uint32_t mls) { return row_hash(p, hBits, mls); }   /* ZSTD_hashPtr, same multipliers */
+static size_t hc_find_best(row_state* ms, const uint8_t* ip, const uint8_t* iLimit, size_t* offBasePtr) {
+    uint32_t const chainSize = 1u << ms->chainLog, chainMask = chainSize - 1;
+    uint32_t const curr = (uint32_t)(ip - ms->base);
+    uint32_t const lowLimit = 2;
+    uint32_t const minChain = curr > chainSize ? curr - chainSize : 0;
+    uint32_t nbAttempts = 1u << ms->searchLog;
+    size_t ml = 4 - 1;
+    uint32_t matchIndex;
+    {   uint32_t idx = ms->nextToUpdate;
+        while (idx < curr) {
+            uint32_t const h = hc_hash(ms->base + idx, ms->hashLog, ms->mls);
+            ms->chainTable[idx & chainMask] = ms->hashTable[h];
+            ms->hashTable[h] = idx;
+            idx++;
+            if (ms->lazySkipping) break;
+        }
+        ms->nextToUpdate = curr;
+        matchIndex = ms->hashTable[hc_hash(ip, ms->hashLog, ms->mls)]; }
+    for (; (matchIndex >= lowLimit) & (nbAttempts > 0); nbAttempts--) {
+        const uint8_t* const match = ms->base + matchIndex;
+        size_t currentMl = 0;
+        if (zso_rd32(match + ml - 3) == zso_rd32(ip + ml - 3)) currentMl = count_match(ip, match, iLimit);
+        if (currentMl > ml) {
+            ml = currentMl;
+            *offBasePtr = (size_t)(curr - matchIndex) + 3;
+            if (ip + currentMl == iLimit) break;
+        }
+        if (matchIndex <= minChain) break;
+        matchIndex = ms->chainTable[matchIndex & chainMask];
+    }
+    return ml;
+}
+static size_t find_best(row_state* ms, const uint8_t* ip, const uint8_t* iLimit, size_t* offBasePtr) {
+    return ms->useRow ? row_find_best(ms, ip, iLimit, offBasePtr) : hc_find_best(ms, ip, iLimit, offBasePtr);
+}
+
 /* ZSTD_compressBlock_lazy_generic :1516-1779; depth 0 = greedy, 1 = lazy, 2 = lazy2.  Returns the trailing literal run. */
-size_t zso_block_lazy_row(void* ssv, uint32_t rep[3], const uint8_t* src, size_t srcSize,
-                          uint32_t* hashTable, uint8_t* tagTable, unsigned hashLog, unsigned searchLog, unsigned minMatch, unsigned depth) {
+size_t zso_block_lazy(void* ssv, uint32_t rep[3], const uint8_t* src, size_t srcSize,
+                      uint32_t* hashTable, uint8_t* tagTable, uint32_t* chainTable, unsigned hashLog, unsigned chainLog, unsigned searchLog,
+                      unsigned minMatch, unsigned depth) {     /* tagTable != NULL: row finder, else hash chain */
     zso_seqStore* const ss = (zso_seqStore*)ssv;
     const uint8_t* const istart = src;
     const uint8_t* ip = istart;
     const uint8_t* anchor = istart;
     const uint8_t* const iend = istart + srcSize;
-    const uint8_t* const ilimit = iend - 8 - ROW_CACHE;
+    int const useRow = tagTable != NULL;
+    const uint8_t* const ilimit = useRow ? iend - 8 - ROW_CACHE : iend - 8;
     const uint8_t* const prefixLowest = src;
     uint32_t offset_1 = rep[0], offset_2 = rep[1], offsetSaved1 = 0, offsetSaved2 = 0;
     row_state ms;
@@ -153,13 +196,14 @@ size_t zso_block_lazy_row(void* ssv, uint32_t rep[3], const uint8_t* src, size_t
     ms.rowLog = searchLog < 4 ? 4 : searchLog > 6 ? 6 : searchLog;
     ms.searchLog = searchLog; ms.rowHashLog = hashLog - ms.rowLog;
     ms.nextToUpdate = 2; ms.lazySkipping = 0;
+    ms.useRow = useRow; ms.chainTable = chainTable; ms.hashLog = hashLog; ms.chainLog = chainLog;
 
     ip += 1;                                            /* dictAndPrefixLength == 0 */
     {   uint32_t const maxRep = (uint32_t)(ip - prefixLowest);
         if (offset_2 > maxRep) { offsetSaved2 = offset_2; offset_2 = 0; }
         if (offset_1 > maxRep) { offsetSaved1 = offset_1; offset_1 = 0; }
     }
-    row_fill_cache(&ms, ms.nextToUpdate, ilimit);
+    if (useRow) row_fill_cache(&ms, ms.nextToUpdate, ilimit);
 
     while (ip < ilimit) {
         size_t matchLength = 0;
@@ -170,7 +214,7 @@ size_t zso_block_lazy_row(void* ssv, uint32_t rep[3], const uint8_t* src, size_t
             if (depth == 0) goto _storeSequence;
         }
         {   size_t offbaseFound = 999999999;
-            size_t const ml2 = row_find_best(&ms, ip, iend, &offbaseFound);
+            size_t const ml2 = find_best(&ms, ip, iend, &offbaseFound);
             if (ml2 > matchLength) { matchLength = ml2; start = ip; offBase = offbaseFound; }
         }
         if (matchLength < 4) {
@@ -189,7 +233,7 @@ size_t zso_block_lazy_row(void* ssv, uint32_t rep[3], const uint8_t* src, size_t
                 if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
             }
             {   size_t ofbCandidate = 999999999;
-                size_t const ml2 = row_find_best(&ms, ip, iend, &ofbCandidate);
+                size_t const ml2 = find_best(&ms, ip, iend, &ofbCandidate);
                 int const gain2 = (int)(ml2 * 4 - zso_highbit32((uint32_t)ofbCandidate));
                 int const gain1 = (int)(matchLength * 4 - zso_highbit32((uint32_t)offBase) + 4);
                 if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; }
@@ -203,7 +247,7 @@ size_t zso_block_lazy_row(void* ssv, uint32_t rep[3], const uint8_t* src, size_t
                     if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
                 }
                 {   size_t ofbCandidate = 999999999;
-                    size_t const ml2 = row_find_best(&ms, ip, iend, &ofbCandidate);
+                    size_t const ml2 = find_best(&ms, ip, iend, &ofbCandidate);
                     int const gain2 = (int)(ml2 * 4 - zso_highbit32((uint32_t)ofbCandidate));
                     int const gain1 = (int)(matchLength * 4 - zso_highbit32((uint32_t)offBase) + 7);
                     if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; }
@@ -219,7 +263,7 @@ size_t zso_block_lazy_row(void* ssv, uint32_t rep[3], const uint8_t* src, size_t
 _storeSequence:
         store_seq(ss, anchor, (size_t)(start - anchor), (uint32_t)offBase, matchLength);
         anchor = ip = start + matchLength;
-        if (ms.lazySkipping) { row_fill_cache(&ms, ms.nextToUpdate, ilimit); ms.lazySkipping = 0; }
+        if (ms.lazySkipping) { if (useRow) row_fill_cache(&ms, ms.nextToUpdate, ilimit); ms.lazySkipping = 0; }
         while (((ip <= ilimit) & (offset_2 > 0)) && (zso_rd32(ip) == zso_rd32(ip - offset_2))) {
             uint32_t tmp;
             matchLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;

@@ -69,6 +69,17 @@ def main():
             fn = f"oneshot_{n:03d}_L{level}.zst"; n += 1
             (HERE / fn).write_bytes(frame)
             man["oneshot"].append({"file": fn, "level": level, "input": spec, "input_sha256": hashlib.sha256(data).hexdigest(), "frame_size": len(frame)})
+    # hash-chain finder: small inputs at levels 4 and 6
+    for spec in specs:
+        data = regenerate_input(spec)
+        if spec["kind"] != "corpus" or spec["size"] not in (1000, 5000, 16384):
+            continue
+        for level in (4, 6):
+            frame = ref_compress(data, level)
+            assert not isinstance(frame, int)
+            fn = f"oneshot_{n:03d}_L{level}.zst"; n += 1
+            (HERE / fn).write_bytes(frame)
+            man["oneshot"].append({"file": fn, "level": level, "input": spec, "input_sha256": hashlib.sha256(data).hexdigest(), "frame_size": len(frame)})
     # decode-only: the reference's streaming path (multi-block, unknown content size, repeat modes)
     multi = {"kind": "multi", "indices": [1, 9, 5, 17], "size": 450000}
     data = regenerate_input(multi)

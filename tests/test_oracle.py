@@ -49,9 +49,8 @@ def test_oracle_matches_compiled_reference(level):
     assert ref().ZSTD_versionString() == b"1.5.7"
     todo = cases.special_cases() + cases.corpus_cases(16) + cases.edge_cases(classes=(0, 4))
     for name, data in todo:
-        if level >= 4 and len(data) <= 16384:
-            # <=16 KB table: greedy/lazy rows use the hash-chain finder (window <= 2^14), level 9+ binary trees: not restated
-            assert oracle_compress(data, level) == -40
+        if level >= 9 and len(data) <= 16384:
+            assert oracle_compress(data, level) == -40     # <=16 KB table, level 9+: binary-tree finder, not restated
             continue
         exp = ref_compress(data, level)
         assert oracle_compress(data, level) == exp, (name, level)

@@ -31,20 +31,20 @@ constexpr u32 ENC_HASHLOG_MAX = 17;     // largest hashLog / chainLog of the sup
 // ZSTD_getCParams_internal (:7759-7782) + ZSTD_adjustCParams_internal (:1472-1609) for a known
 // srcSize <= 128 KB, no dictionary.  Returns false when the level selects a parser this build lacks.
 ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize) {
-    // rows 0..10 of the "<=128 KB" table and 0..3 of the "<=16 KB" table (clevels.h:78-90,104-109).  Levels 5..10 use
-    // greedy / lazy / lazy2 with the row-based match finder, which the reference selects for windowLog > 14
-    // (ZSTD_resolveRowMatchFinderMode, zstd_compress.c:238-245), i.e. for every srcSize > 16 KB; the hash-chain and
-    // binary-tree finders of the small-input rows are not built.
+    // rows 0..10 of the "<=128 KB" table and 0..8 of the "<=16 KB" table (clevels.h:78-90,104-114).  greedy / lazy / lazy2
+    // run with the row-based match finder when windowLog > 14 (ZSTD_resolveRowMatchFinderMode, zstd_compress.c:238-245),
+    // i.e. for every srcSize > 16 KB, and with the hash-chain finder below; the binary-tree rows are not built.
     const CParams t128[11] = { {17,12,12,1,5,1,S_fast}, {17,12,13,1,6,0,S_fast}, {17,13,15,1,5,0,S_fast}, {17,15,16,2,5,0,S_dfast}, {17,17,17,2,4,0,S_dfast},
                                {17,16,17,3,4,2,S_greedy}, {17,16,17,3,4,4,S_lazy}, {17,16,17,3,4,8,S_lazy2}, {17,16,17,4,4,8,S_lazy2}, {17,16,17,5,4,8,S_lazy2},
                                {17,16,17,6,4,8,S_lazy2} };
-    const CParams t16[4] = { {14,12,13,1,5,1,S_fast}, {14,14,15,1,5,0,S_fast}, {14,14,15,1,4,0,S_fast}, {14,14,15,2,4,0,S_dfast} };
+    const CParams t16[9] = { {14,12,13,1,5,1,S_fast}, {14,14,15,1,5,0,S_fast}, {14,14,15,1,4,0,S_fast}, {14,14,15,2,4,0,S_dfast},
+                             {14,14,14,4,4,2,S_greedy}, {14,14,14,3,4,4,S_lazy}, {14,14,14,4,4,8,S_lazy2}, {14,14,14,6,4,8,S_lazy2}, {14,14,14,8,4,8,S_lazy2} };
     if (srcSize > BLOCKSIZE_MAX) return false;
     int row = level;
     if (level == 0) row = 3;
     if (level < 0) row = 0;
     bool const small = srcSize <= 16 * 1024;
-    if (row > (small ? 3 : 10)) return false;
+    if (row > (small ? 8 : 10)) return false;
     CParams cp = small ? t16[row] : t128[row];
     if (level < 0) { int const l = level < -(1 << 17) ? -(1 << 17) : level; cp.targetLength = (u32)(-l); }
     u32 const tSize = (u32)srcSize;
@@ -1322,6 +1322,7 @@ struct RowState {
     u32* hashTable; u8* tagTable; const u8* base;
     u32 hashCache[8];
     u32 rowHashLog, rowLog, searchLog, mls, nextToUpdate; bool lazySkipping;
+    bool useRow; u32* chainTable; u32 hashLog, chainLog;      // hash-chain finder (window <= 2^14)
 };
 ZB_HD u32 row_hash(const u8* p, u32 hBits, u32 mls) {
     switch (mls) {
@@ -1410,15 +1411,53 @@ ZB_HDN size_t row_find_best(RowState& ms, const u8* ip, const u8* iLimit, size_t
     }
     return ml;
 }
-ZB_HDN u32 parse_lazy_row(const EncWork& W, const u8* src, size_t srcSize, u32 hashLog, u32 searchLog, u32 minMatch, u32 depth, u32* lastLL) {
+// ZSTD_HcFindBestMatch :667-733 with ZSTD_insertAndFindFirstIndex_internal :632-657 (noDict): hashTable = W.hashLong,
+// chainTable = W.hashSmall (1 << chainLog cells).
+ZB_HDN size_t hc_find_best(RowState& ms, const u8* ip, const u8* iLimit, size_t* offBasePtr) {
+    u32 const chainSize = 1u << ms.chainLog, chainMask = chainSize - 1;
+    u32 const curr = (u32)(ip - ms.base);
+    u32 const lowLimit = 2;
+    u32 const minChain = curr > chainSize ? curr - chainSize : 0;
+    u32 nbAttempts = 1u << ms.searchLog;
+    size_t ml = 4 - 1;
+    u32 matchIndex;
+    {   u32 idx = ms.nextToUpdate;
+        while (idx < curr) {
+            u32 const h = row_hash(ms.base + idx, ms.hashLog, ms.mls);
+            ms.chainTable[idx & chainMask] = ms.hashTable[h];
+            ms.hashTable[h] = idx;
+            idx++;
+            if (ms.lazySkipping) break;
+        }
+        ms.nextToUpdate = curr;
+        matchIndex = ms.hashTable[row_hash(ip, ms.hashLog, ms.mls)]; }
+    for (; (matchIndex >= lowLimit) && (nbAttempts > 0); nbAttempts--) {
+        const u8* const match = ms.base + matchIndex;
+        size_t currentMl = 0;
+        if (load32(match + ml - 3) == load32(ip + ml - 3)) currentMl = count_match(ip, match, iLimit);
+        if (currentMl > ml) {
+            ml = currentMl;
+            *offBasePtr = (size_t)(curr - matchIndex) + 3;
+            if (ip + currentMl == iLimit) break;
+        }
+        if (matchIndex <= minChain) break;
+        matchIndex = ms.chainTable[matchIndex & chainMask];
+    }
+    return ml;
+}
+ZB_HD size_t lazy_find_best(RowState& ms, const u8* ip, const u8* iLimit, size_t* offBasePtr) {
+    return ms.useRow ? row_find_best(ms, ip, iLimit, offBasePtr) : hc_find_best(ms, ip, iLimit, offBasePtr);
+}
+ZB_HDN u32 parse_lazy(const EncWork& W, const u8* src, size_t srcSize, u32 hashLog, u32 chainLog, u32 searchLog, u32 minMatch, u32 depth, bool useRow, u32* lastLL) {
     const u8* const istart = src;
     const u8* ip = istart;
     const u8* anchor = istart;
     const u8* const iend = istart + srcSize;
-    const u8* const ilimit = iend - 8 - 8;
+    const u8* const ilimit = useRow ? iend - 8 - 8 : iend - 8;
     const u8* const prefixLowest = src;
     u32 offset_1 = 1, offset_2 = 4, nbSeq = 0;
     RowState ms;
+    ms.useRow = useRow; ms.chainTable = W.hashSmall; ms.hashLog = hashLog; ms.chainLog = chainLog;
     ms.hashTable = W.hashLong; ms.tagTable = reinterpret_cast<u8*>(W.hashSmall); ms.base = src - 2;
     ms.mls = minMatch < 4 ? 4 : minMatch > 6 ? 6 : minMatch;
     ms.rowLog = searchLog < 4 ? 4 : searchLog > 6 ? 6 : searchLog;
@@ -1428,7 +1467,7 @@ ZB_HDN u32 parse_lazy_row(const EncWork& W, const u8* src, size_t srcSize, u32 h
     {   u32 const maxRep = (u32)(ip - prefixLowest);
         if (offset_2 > maxRep) offset_2 = 0;
         if (offset_1 > maxRep) offset_1 = 0; }
-    row_fill_cache(ms, ms.nextToUpdate, ilimit);
+    if (useRow) row_fill_cache(ms, ms.nextToUpdate, ilimit);
     while (ip < ilimit) {
         size_t matchLength = 0;
         size_t offBase = 1;
@@ -1440,7 +1479,7 @@ ZB_HDN u32 parse_lazy_row(const EncWork& W, const u8* src, size_t srcSize, u32 h
         }
         if (!store) {
             {   size_t offbaseFound = 999999999;
-                size_t const ml2 = row_find_best(ms, ip, iend, &offbaseFound);
+                size_t const ml2 = lazy_find_best(ms, ip, iend, &offbaseFound);
                 if (ml2 > matchLength) { matchLength = ml2; start = ip; offBase = offbaseFound; } }
             if (matchLength < 4) {
                 size_t const step = ((size_t)(ip - anchor) >> 8) + 1;      // kSearchStrength
@@ -1458,7 +1497,7 @@ ZB_HDN u32 parse_lazy_row(const EncWork& W, const u8* src, size_t srcSize, u32 h
                     if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
                 }
                 {   size_t ofbCandidate = 999999999;
-                    size_t const ml2 = row_find_best(ms, ip, iend, &ofbCandidate);
+                    size_t const ml2 = lazy_find_best(ms, ip, iend, &ofbCandidate);
                     int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofbCandidate));
                     int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 4);
                     if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; } }
@@ -1471,7 +1510,7 @@ ZB_HDN u32 parse_lazy_row(const EncWork& W, const u8* src, size_t srcSize, u32 h
                         if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
                     }
                     {   size_t ofbCandidate = 999999999;
-                        size_t const ml2 = row_find_best(ms, ip, iend, &ofbCandidate);
+                        size_t const ml2 = lazy_find_best(ms, ip, iend, &ofbCandidate);
                         int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofbCandidate));
                         int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 7);
                         if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; } }
@@ -1486,7 +1525,7 @@ ZB_HDN u32 parse_lazy_row(const EncWork& W, const u8* src, size_t srcSize, u32 h
         }
         W.seqLL[nbSeq] = (u32)(start - anchor); W.seqOF[nbSeq] = (u32)offBase; W.seqML[nbSeq] = (u32)matchLength; nbSeq++;
         anchor = ip = start + matchLength;
-        if (ms.lazySkipping) { row_fill_cache(ms, ms.nextToUpdate, ilimit); ms.lazySkipping = false; }
+        if (ms.lazySkipping) { if (useRow) row_fill_cache(ms, ms.nextToUpdate, ilimit); ms.lazySkipping = false; }
         while (((ip <= ilimit) && (offset_2 > 0)) && (load32(ip) == load32(ip - offset_2))) {
             matchLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
             u32 const tmp = offset_2; offset_2 = offset_1; offset_1 = tmp;
@@ -1513,7 +1552,9 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
     if (srcSize < 7) return 0;
     {   // fresh tables: zero the used part (16-byte stores; the workspace is 16-byte aligned)
         u32 const nL = (1u << cp.hashLog) / 4;
-        u32 const nS = (cp.strategy == S_dfast) ? (1u << cp.chainLog) / 4 : (cp.strategy >= S_greedy) ? (1u << cp.hashLog) / 16 : 0;   // tag bytes
+        u32 const nS = (cp.strategy == S_dfast) ? (1u << cp.chainLog) / 4                               // short-hash table
+                     : (cp.strategy >= S_greedy) ? (cp.windowLog > 14 ? (1u << cp.hashLog) / 16          // tag bytes of the row finder
+                                                                        : (1u << cp.chainLog) / 4) : 0;  // chain table
         struct alignas(16) Q { u32 a, b, c, d; };
         Q* const qL = reinterpret_cast<Q*>(W.hashLong); Q* const qS = reinterpret_cast<Q*>(W.hashSmall);
         Q const z = { 0, 0, 0, 0 };
@@ -1525,7 +1566,7 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
         nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
     } else {
         if (w.lane == 0) {
-            if (cp.strategy >= S_greedy) nbSeq = parse_lazy_row(W, src, srcSize, cp.hashLog, cp.searchLog, cp.minMatch, cp.strategy - S_greedy, &lastLL);
+            if (cp.strategy >= S_greedy) nbSeq = parse_lazy(W, src, srcSize, cp.hashLog, cp.chainLog, cp.searchLog, cp.minMatch, cp.strategy - S_greedy, cp.windowLog > 14, &lastLL);
             else if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
             else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
         }
