@@ -32,6 +32,23 @@ __global__ void k_probe(u32* __restrict__ tab, u64 mask, int iters, u32* out) {
     }
     if (acc == 0x12345678) *out = acc;
 }
+__global__ void k_exch(u32* __restrict__ tab, u64 mask, int iters, u32* out) {      // one atomic instead of read + write
+    u64 x = (u64)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ULL + 12345;
+    u32 acc = 0;
+    for (int i = 0; i < iters; i++) {
+        x = x * 6364136223846793005ULL + 1442695040888963407ULL;
+        u64 const idx = (x >> 20) & mask;
+        acc += atomicExch(tab + idx, (u32)i);
+    }
+    if (acc == 0x12345678) *out = acc;
+}
+__global__ void k_wonly(u32* __restrict__ tab, u64 mask, int iters, u32* out) {     // blind 4-byte writes
+    u64 x = (u64)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ULL + 12345;
+    for (int i = 0; i < iters; i++) {
+        x = x * 6364136223846793005ULL + 1442695040888963407ULL;
+        tab[(x >> 20) & mask] = (u32)i;
+    }
+}
 template <int MODE, bool WRITE> float run(u32* tab, u64 mask, int blocks, int iters, u32* out) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     k_probe<MODE, WRITE><<<blocks, 256>>>(tab, mask, iters / 8, out);
@@ -48,8 +65,13 @@ int main(int argc, char** argv) {
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int const blocks = sms * 8, iters = 2048;
     double const probes = (double)blocks * 256 * iters;
+    {   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); float ms;
+        k_exch<<<blocks, 256>>>(tab, words - 1, iters / 8, out); cudaEventRecord(a); k_exch<<<blocks, 256>>>(tab, words - 1, iters, out); cudaEventRecord(b); cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b); printf("atomicExch (old value used)        %8.2f ms  %7.2f G probes/s\n", ms, probes / ms / 1e6);
+        k_wonly<<<blocks, 256>>>(tab, words - 1, iters / 8, out); cudaEventRecord(a); k_wonly<<<blocks, 256>>>(tab, words - 1, iters, out); cudaEventRecord(b); cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b); printf("blind 4-byte writes                %8.2f ms  %7.2f G probes/s\n", ms, probes / ms / 1e6); }
     const char* names[] = {"ld", "ld.cg", "ld.cs", "ld.lu", "ld.cv", "no_alloc+evict_first", "no_alloc+evict_last"};
-    for (int gran : {0, 32, 64, 128}) {
+    for (int gran : {0, 32}) {
         if (gran) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); size_t g = 0; cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity);
             printf("set L2 fetch granularity %d -> %s, now %zu\n", gran, cudaGetErrorString(e), g); }
         else { size_t g = 0; cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); printf("default L2 fetch granularity %zu\n", g); }

@@ -1313,6 +1313,136 @@ ZB_HDN u32 parse_fast(const EncWork& W, const u8* src, size_t srcSize, u32 hlog,
     return nbSeq;
 }
 
+// Cooperative version of parse_fast (ZSTD_compressBlock_fast_noDict_generic, zstd_fast.c:190-423) for levels 1, 2 and
+// the negative levels.  The reference visits positions in pairs: iteration i hashes a_i and a_i + 1 and tests the
+// repcode at r_i = a_{i+1} (the next pair), in the order [rep @ r_i] -> [hash @ a_i] -> [hash @ a_i + 1]; every visited
+// position is written to the table before the next one is read.  Here lane 2i / 2i+1 take a_i / a_i + 1 of up to 16
+// consecutive iterations: table reads are forwarded between lanes exactly like in parse_dfast_warp, the first event
+// in the reference's order ends the batch, and only what the serial code would have written is committed.
+// Iteration state (a, r, s, nextStep): rep test at r, then a' = r, r' = a' + s, and s grows when r' reaches nextStep
+// (the reference computes ip2 before it bumps `step`, hence the explicit r).  Cells carry a 14-bit fingerprint.
+template <class C>
+ZB_HDN u32 parse_fast_warp(const C& w, const EncWork& W, const u8* src, size_t srcSize, u32 hlog, u32 mls, u32 targetLength, u32* lastLL) {
+    u32* const T = W.hashLong;
+    u32 const stepSize = targetLength + !targetLength + 1;
+    int const n = (int)srcSize, ilimit = n - 8;
+    int ip0 = 1, anchor = 0;
+    u32 rep1 = 1, rep2 = 0, nbSeq = 0;          // {1,4,8} clipped by maxRep = 1 at position 1
+    u32 const lane = (u32)w.lane;
+    int const it = (int)(lane >> 1); bool const odd = (lane & 1) != 0;
+    u32 est4 = 4 * 3;
+    bool done = false;
+    while (!done) {   // _start: one iteration per stored match
+        if (ip0 + (int)stepSize + 1 >= ilimit) break;
+        int a = ip0, r = ip0 + (int)stepSize, nextStep = ip0 + 128; u32 s = stepSize;      // state of the first iteration
+        u32 nIt = 1;
+        {   u32 const want = (est4 + 7) / 8;
+            while (nIt < want && 2 * nIt < (u32)C::W) nIt *= 2; }
+        u32 runIt = 0;
+        int evKey = -1, e = -1;
+        // per-lane values of the deciding batch
+        int ai = 0, ri = 0; u32 si = 0; int nsi = 0; u64 d = 0; u32 h = 0, idx = 0; int p = 0;
+        for (;;) {   // batches of nIt iterations
+            // my iteration's start state (ai, ri, si, nsi) and its end state (ae, re, se, nse)
+            ai = a; ri = r; si = s; nsi = nextStep;
+            if (r + (int)(C::W / 2 + 1) * (int)s < nextStep) { if (it > 0) { ai = r + (it - 1) * (int)s; ri = r + it * (int)s; } }
+            else for (int j = 0; j < it; j++) { ai = ri; ri = ai + (int)si; if (ri >= nsi) { si++; nsi += 128; } }
+            int ae = ri, re = ae + (int)si; u32 se = si; int nse = nsi;
+            if (re >= nse) { se++; nse += 128; }
+            bool const valid = (u32)it < nIt && ri + 1 < ilimit;        // monotone in it
+            bool const active = valid && lane < (u32)C::W;
+            p = ai + (odd ? 1 : 0);
+            d = active ? load64(src + p) : 0;
+            h = hashSv(d, hlog, mls);
+            u32 const myTag = tag4((u32)d);
+            u32 const tv = active ? ld_probe32(T + h) : 0;
+            u32 const mH = w.match_any(active ? h : (0x80000000u | lane));
+            u32 const lowH = mH & ((1u << lane) - 1);
+            int const pLow = w.shfl(p, lowH ? (int)highbit32(lowH) : (int)lane);
+            idx = lowH ? (u32)pLow + 2 : (tv & CELL_IDX_MASK);
+            bool const plaus = idx >= 2 && (lowH || (tv >> 18) == myTag);
+            bool const hashOk = active && plaus && (load32(src + (idx - 2)) == (u32)d);
+            bool const repOk = active && !odd && rep1 > 0 && (load32(src + ri) == load32(src + ri - (int)rep1));
+            u32 const repMask = w.ballot(repOk), hashMask = w.ballot(hashOk);
+            u32 const nValid = popc32(w.ballot(active && !odd));
+            int const keyR = repMask ? 3 * (int)(ctz32(repMask) >> 1) : 0x7FFFFFFF;
+            int const lh = hashMask ? (int)ctz32(hashMask) : 0;
+            int const keyH = hashMask ? 3 * (lh >> 1) + 1 + (lh & 1) : 0x7FFFFFFF;
+            evKey = keyR < keyH ? keyR : keyH;
+            if (evKey == 0x7FFFFFFF) evKey = -1;
+            e = evKey >= 0 ? evKey / 3 : -1;
+            // commits: every active lane up to 2e+1 (all of them without event); per cell only the last writer
+            int const lastLane = evKey >= 0 ? 2 * e + 1 : 2 * (int)nValid - 1;
+            if (active && (int)lane <= lastLane) {
+                u32 const later = ((lastLane >= 31) ? 0xFFFFFFFFu : ((2u << lastLane) - 1)) & ~((2u << lane) - 1);
+                if (!(mH & later)) T[h] = cell((u32)p + 2, myTag);
+            }
+            w.sync();
+            runIt += evKey >= 0 ? (u32)e + 1 : nValid;
+            if (evKey >= 0) break;
+            if (nValid < nIt) { done = true; break; }          // ran into ilimit: the reference leaves the search loop for good
+            {   int const L = 2 * ((int)nValid - 1);
+                a = w.shfl(ae, L); r = w.shfl(re, L); s = w.shfl(se, L); nextStep = w.shfl(nse, L); }
+            if (r + 1 >= ilimit) { done = true; break; }
+            nIt = 2 * nIt * 2 <= (u32)C::W ? nIt * 2 : (u32)C::W / 2;
+        }
+        if (done || evKey < 0) break;
+        est4 = (3 * est4 + 4 * 2 * (runIt < 32 ? runIt : 32)) / 4;
+        // ---- event in iteration e
+        int const kindE = evKey - 3 * e;                      // 0 rep @ r_e, 1 hash @ a_e, 2 hash @ a_e + 1
+        int const aE = w.shfl(ai, 2 * e), rE = w.shfl(ri, 2 * e); u32 const sE = w.shfl(si, 2 * e);
+        u32 mLength; int mpos, cur;
+        if (kindE == 2 && sE <= 4) {                          // :"if (step <= 4) hashTable[hash1] = ip1" with ip1 == r_e
+            if (lane == 0) { u64 const dr = load64(src + rE); T[hashSv(dr, hlog, mls)] = cell((u32)rE + 2, tag4((u32)dr)); }
+        }
+        if (kindE == 0) {
+            cur = aE; ip0 = rE; mpos = ip0 - (int)rep1;
+            u32 const back = (src[ip0 - 1] == src[mpos - 1]) ? 1u : 0u;
+            ip0 -= (int)back; mpos -= (int)back;
+            mLength = 4 + back;
+            mLength += wcount(w, src, (u32)n, (u32)ip0 + mLength, (u32)mpos + mLength);
+            if (lane == 0) { W.seqLL[nbSeq] = (u32)(ip0 - anchor); W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = mLength; }
+        } else {
+            int const le = 2 * e + (kindE == 2 ? 1 : 0);
+            ip0 = aE + (kindE == 2 ? 1 : 0); cur = ip0;
+            mpos = (int)w.shfl(idx, le) - 2;
+            rep2 = rep1; rep1 = (u32)(ip0 - mpos);
+            u32 const maxBack = (u32)(ip0 - anchor) < (u32)mpos ? (u32)(ip0 - anchor) : (u32)mpos;
+            u32 const back = maxBack ? wcatchup(w, src, (u32)ip0, (u32)mpos, maxBack) : 0;
+            u32 const fwd = wcount(w, src, (u32)n, (u32)ip0 + 4, (u32)mpos + 4);
+            ip0 -= (int)back; mLength = 4 + back + fwd;
+            if (lane == 0) { W.seqLL[nbSeq] = (u32)(ip0 - anchor); W.seqOF[nbSeq] = rep1 + 3; W.seqML[nbSeq] = mLength; }
+        }
+        nbSeq++;
+        ip0 += (int)mLength; anchor = ip0;
+        w.sync();
+        if (ip0 <= ilimit) {
+            if (lane == 0) {   // :"Fill table and check for immediate repcode"
+                u64 const dA = load64(src + cur + 2), dB = load64(src + ip0 - 2);
+                T[hashSv(dA, hlog, mls)] = cell((u32)cur + 2 + 2, tag4((u32)dA));
+                T[hashSv(dB, hlog, mls)] = cell((u32)ip0 - 2 + 2, tag4((u32)dB));
+            }
+            w.sync();
+            if (rep2 > 0) {
+                while ((ip0 <= ilimit) && (load32(src + ip0) == load32(src + ip0 - (int)rep2))) {
+                    u32 const rLength = wcount(w, src, (u32)n, (u32)ip0 + 4, (u32)ip0 + 4 - rep2) + 4;
+                    { u32 const t = rep2; rep2 = rep1; rep1 = t; }
+                    if (lane == 0) {
+                        u64 const d0 = load64(src + ip0);
+                        T[hashSv(d0, hlog, mls)] = cell((u32)ip0 + 2, tag4((u32)d0));
+                        W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength;
+                    }
+                    nbSeq++; ip0 += (int)rLength; anchor = ip0;
+                    w.sync();
+                }
+            }
+        }
+    }
+    w.sync();
+    *lastLL = (u32)(n - anchor);
+    return nbSeq;
+}
+
 // ZSTD_compressBlock_lazy_generic (N/compress/zstd_lazy.c:1516-1779; depth 0 greedy, 1 lazy, 2 lazy2) with the
 // row-based match finder (ZSTD_RowFindBestMatch :1141-1283, ZSTD_row_update_internal :885-943, hash cache :837-878,
 // ZSTD_row_nextIndex :798-803, match mask :1061-1121), fresh frame, no dictionary.  Serial: call from one lane.
@@ -1564,6 +1694,8 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
     u32 nbSeq = 0, lastLL = 0;
     if (C::W > 1 && cp.strategy == S_dfast) {
         nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
+    } else if (C::W > 1 && cp.strategy == S_fast) {
+        nbSeq = parse_fast_warp(w, W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
     } else {
         if (w.lane == 0) {
             if (cp.strategy >= S_greedy) nbSeq = parse_lazy(W, src, srcSize, cp.hashLog, cp.chainLog, cp.searchLog, cp.minMatch, cp.strategy - S_greedy, cp.windowLog > 14, &lastLL);
