@@ -87,9 +87,9 @@ ZSTDB200_API size_t ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* cctx, unsigned long l
  *   ZSTD_decompress      <- N/jni_zstd.c:62
  * src/dst are caller-owned host memory borrowed for the duration of the call.
  * Compression scope of this build: srcSize <= 128 KB per call (one block => one frame), levels whose
- * parameters select the fast / dfast parsers or greedy / lazy / lazy2 (row-based match finder for inputs > 16 KB,
- * hash chain below): levels 1..10 and the negative levels for srcSize > 16 KB, levels 1..8 and negatives for
- * srcSize <= 16 KB; the binary-tree finders (levels >= 11, levels 9..10 on inputs <= 16 KB) return
+ * parameters select the fast / dfast parsers, greedy / lazy / lazy2 (row-based match finder for inputs > 16 KB,
+ * hash chain below) or btlazy2 (binary tree): the negative levels and levels 1..12 for srcSize > 16 KB, 1..10 for
+ * srcSize <= 16 KB; the optimal-parser strategies above return
  * ZSTD_error_parameter_unsupported rather than silently producing different bytes.
  * Decompression accepts any zstd stream without dictionary (multi-block, multi-frame, skippable, checksum). */
 ZSTDB200_API size_t ZSTD_compress2(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize);

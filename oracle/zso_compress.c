@@ -869,7 +869,7 @@ size_t zso_block_fast(zso_seqStore* ss, uint32_t rep[3], const uint8_t* src, siz
 /* greedy / lazy / lazy2 live in zso_lazy.c: row-based match finder (levels 5..10, srcSize > 16 KB) or hash chain (levels 4..8, <= 16 KB) */
 size_t zso_block_lazy(void* ss, uint32_t rep[3], const uint8_t* src, size_t srcSize,
                       uint32_t* hashTable, uint8_t* tagTable, uint32_t* chainTable, unsigned hashLog, unsigned chainLog, unsigned searchLog,
-                      unsigned minMatch, unsigned depth);
+                      unsigned minMatch, unsigned depth, int binaryTree);
 
 /* ---------------------------------------------------------------- frame */
 size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t srcSize, int level) {
@@ -877,7 +877,7 @@ size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t src
     if (zso_getCParams(&cp, level, srcSize)) return ZSO_ERROR(parameter_unsupported);
     /* supported block compressors: fast, dfast, greedy/lazy/lazy2 (row match finder when windowLog > 14,
      * ZSTD_resolveRowMatchFinderMode zstd_compress.c:238-245, else hash chain); the binary-tree finders are not restated */
-    if (cp.strategy > ZSO_lazy2) return ZSO_ERROR(parameter_unsupported);
+    if (cp.strategy > ZSO_btlazy2) return ZSO_ERROR(parameter_unsupported);      /* btopt and up: optimal parser, not restated */
     if (dstCapacity < 18) return ZSO_ERROR(dstSize_tooSmall);   /* ZSTD_FRAMEHEADERSIZE_MAX :4716 */
     /* ZSTD_writeFrameHeader :4695-4743 : contentSizeFlag=1, no checksum, no dictID; windowSize >= srcSize => singleSegment */
     {   uint32_t const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256);
@@ -902,11 +902,12 @@ size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t src
             ss.lit = (uint8_t*)malloc(srcSize + 8); ss.litSize = 0;
             if (!hashLong || !hashSmall || !ss.seq || !ss.lit) { free(hashLong); free(hashSmall); free(ss.seq); free(ss.lit); return ZSO_ERROR(GENERIC); }
             if (cp.strategy >= ZSO_greedy) {
-                int const useRow = cp.windowLog > 14;
+                int const bt = cp.strategy == ZSO_btlazy2;
+                int const useRow = !bt && cp.windowLog > 14;
                 uint8_t* const tagTable = useRow ? (uint8_t*)calloc((size_t)1 << cp.hashLog, 1) : NULL;
                 if (useRow && !tagTable) { free(hashLong); free(hashSmall); free(ss.seq); free(ss.lit); return ZSO_ERROR(GENERIC); }
                 lastLL = zso_block_lazy(&ss, rep, src, srcSize, hashLong, tagTable, hashSmall /* chain table, 1 << chainLog */, cp.hashLog, cp.chainLog,
-                                        cp.searchLog, cp.minMatch, cp.strategy - ZSO_greedy);
+                                        cp.searchLog, cp.minMatch, bt ? 2 : cp.strategy - ZSO_greedy, bt);
                 free(tagTable);
             }
             else if (cp.strategy == ZSO_dfast) lastLL = block_dfast(&ss, rep, src, srcSize, hashLong, cp.hashLog, hashSmall, cp.chainLog, cp.minMatch);

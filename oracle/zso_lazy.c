@@ -8,6 +8,8 @@
  *   ZSTD_row_nextIndex :798-803, ZSTD_row_getMatchMask :1061-1121 (any of its SIMD/SWAR variants: same mask)
  * and with the hash-chain finder the reference uses when the window is <= 2^14 (inputs <= 16 KB, levels 4..8):
  *   ZSTD_HcFindBestMatch :667-733, ZSTD_insertAndFindFirstIndex_internal :632-657
+ * and with the binary-tree finder of btlazy2 (levels 9..10 on inputs <= 16 KB, levels 11..12):
+ *   ZSTD_BtFindBestMatch :399-408, ZSTD_updateDUBT :29-65, ZSTD_insertDUBT1 :74-163, ZSTD_DUBT_findBestMatch :243-395
  * Index convention as in the other parsers: index = position + 2, zeroed cells are "nothing".
  * The hash salt is 0: the salt is XORed before the shift, so it only permutes rows and tags and the emitted
  * sequences do not depend on it; tag rows start zeroed like a fresh context.
@@ -173,14 +175,130 @@ static size_t hc_find_best(row_state* ms, const uint8_t* ip, const uint8_t* iLim
     }
     return ml;
 }
+/* ---- binary tree of the "dual unsorted" kind (DUBT); bt = chainTable as pairs {smaller, larger}, btLog = chainLog - 1 */
+#define DUBT_UNSORTED_MARK 1
+static void dubt_update(row_state* ms, const uint8_t* ip) {            /* ZSTD_updateDUBT :29-65 */
+    uint32_t const btMask = (1u << (ms->chainLog - 1)) - 1;
+    uint32_t const target = (uint32_t)(ip - ms->base);
+    uint32_t idx = ms->nextToUpdate;
+    for (; idx < target; idx++) {
+        uint32_t const h = hc_hash(ms->base + idx, ms->hashLog, ms->mls);
+        uint32_t const matchIndex = ms->hashTable[h];
+        uint32_t* const nextCandidatePtr = ms->chainTable + 2 * (idx & btMask);
+        ms->hashTable[h] = idx;
+        nextCandidatePtr[0] = matchIndex;
+        nextCandidatePtr[1] = DUBT_UNSORTED_MARK;
+    }
+    ms->nextToUpdate = target;
+}
+static void dubt_insert1(row_state* ms, uint32_t curr, const uint8_t* iend, uint32_t nbCompares, uint32_t btLow) {   /* ZSTD_insertDUBT1 :74-163 */
+    uint32_t* const bt = ms->chainTable;
+    uint32_t const btMask = (1u << (ms->chainLog - 1)) - 1;
+    size_t commonLengthSmaller = 0, commonLengthLarger = 0;
+    const uint8_t* const ip = ms->base + curr;
+    uint32_t* smallerPtr = bt + 2 * (curr & btMask);
+    uint32_t* largerPtr = smallerPtr + 1;
+    uint32_t matchIndex = *smallerPtr;
+    uint32_t dummy32;
+    uint32_t const windowLow = 2;
+    for (; nbCompares && (matchIndex > windowLow); --nbCompares) {
+        uint32_t* const nextPtr = bt + 2 * (matchIndex & btMask);
+        size_t matchLength = commonLengthSmaller < commonLengthLarger ? commonLengthSmaller : commonLengthLarger;
+        const uint8_t* const match = ms->base + matchIndex;
+        matchLength += count_match(ip + matchLength, match + matchLength, iend);
+        if (ip + matchLength == iend) break;
+        if (match[matchLength] < ip[matchLength]) {
+            *smallerPtr = matchIndex;
+            commonLengthSmaller = matchLength;
+            if (matchIndex <= btLow) { smallerPtr = &dummy32; break; }
+            smallerPtr = nextPtr + 1;
+            matchIndex = nextPtr[1];
+        } else {
+            *largerPtr = matchIndex;
+            commonLengthLarger = matchLength;
+            if (matchIndex <= btLow) { largerPtr = &dummy32; break; }
+            largerPtr = nextPtr;
+            matchIndex = nextPtr[0];
+        }
+    }
+    *smallerPtr = *largerPtr = 0;
+}
+static size_t bt_find_best(row_state* ms, const uint8_t* ip, const uint8_t* iend, size_t* offBasePtr) {   /* :399-408 + :243-395 */
+    uint32_t* const bt = ms->chainTable;
+    uint32_t const btMask = (1u << (ms->chainLog - 1)) - 1;
+    uint32_t const curr = (uint32_t)(ip - ms->base);
+    uint32_t const windowLow = 2;
+    uint32_t const btLow = (btMask >= curr) ? 0 : curr - btMask;
+    uint32_t const unsortLimit = btLow > windowLow ? btLow : windowLow;
+    uint32_t h, matchIndex, nbCompares = 1u << ms->searchLog, nbCandidates = nbCompares, previousCandidate = 0;
+    uint32_t* nextCandidate; uint32_t* unsortedMark;
+    if (ip < ms->base + ms->nextToUpdate) return 0;      /* skipped area */
+    dubt_update(ms, ip);
+    h = hc_hash(ip, ms->hashLog, ms->mls);
+    matchIndex = ms->hashTable[h];
+    nextCandidate = bt + 2 * (matchIndex & btMask); unsortedMark = nextCandidate + 1;
+    while ((matchIndex > unsortLimit) && (*unsortedMark == DUBT_UNSORTED_MARK) && (nbCandidates > 1)) {
+        *unsortedMark = previousCandidate;
+        previousCandidate = matchIndex;
+        matchIndex = *nextCandidate;
+        nextCandidate = bt + 2 * (matchIndex & btMask); unsortedMark = nextCandidate + 1;
+        nbCandidates--;
+    }
+    if ((matchIndex > unsortLimit) && (*unsortedMark == DUBT_UNSORTED_MARK)) *nextCandidate = *unsortedMark = 0;
+    matchIndex = previousCandidate;
+    while (matchIndex) {
+        uint32_t* const nextCandidateIdxPtr = bt + 2 * (matchIndex & btMask) + 1;
+        uint32_t const nextCandidateIdx = *nextCandidateIdxPtr;
+        dubt_insert1(ms, matchIndex, iend, nbCandidates, unsortLimit);
+        matchIndex = nextCandidateIdx;
+        nbCandidates++;
+    }
+    {   size_t commonLengthSmaller = 0, commonLengthLarger = 0, bestLength = 0;
+        uint32_t* smallerPtr = bt + 2 * (curr & btMask);
+        uint32_t* largerPtr = smallerPtr + 1;
+        uint32_t matchEndIdx = curr + 8 + 1;
+        uint32_t dummy32;
+        matchIndex = ms->hashTable[h];
+        ms->hashTable[h] = curr;
+        for (; nbCompares && (matchIndex > windowLow); --nbCompares) {
+            uint32_t* const nextPtr = bt + 2 * (matchIndex & btMask);
+            size_t matchLength = commonLengthSmaller < commonLengthLarger ? commonLengthSmaller : commonLengthLarger;
+            const uint8_t* const match = ms->base + matchIndex;
+            matchLength += count_match(ip + matchLength, match + matchLength, iend);
+            if (matchLength > bestLength) {
+                if (matchLength > matchEndIdx - matchIndex) matchEndIdx = matchIndex + (uint32_t)matchLength;
+                if ((4 * (int)(matchLength - bestLength)) > (int)(zso_highbit32(curr - matchIndex + 1) - zso_highbit32((uint32_t)*offBasePtr))) {
+                    bestLength = matchLength; *offBasePtr = (size_t)(curr - matchIndex) + 3; }
+                if (ip + matchLength == iend) break;
+            }
+            if (match[matchLength] < ip[matchLength]) {
+                *smallerPtr = matchIndex;
+                commonLengthSmaller = matchLength;
+                if (matchIndex <= btLow) { smallerPtr = &dummy32; break; }
+                smallerPtr = nextPtr + 1;
+                matchIndex = nextPtr[1];
+            } else {
+                *largerPtr = matchIndex;
+                commonLengthLarger = matchLength;
+                if (matchIndex <= btLow) { largerPtr = &dummy32; break; }
+                largerPtr = nextPtr;
+                matchIndex = nextPtr[0];
+            }
+        }
+        *smallerPtr = *largerPtr = 0;
+        ms->nextToUpdate = matchEndIdx - 8;
+        return bestLength;
+    }
+}
 static size_t find_best(row_state* ms, const uint8_t* ip, const uint8_t* iLimit, size_t* offBasePtr) {
+    if (ms->useRow == 2) return bt_find_best(ms, ip, iLimit, offBasePtr);
     return ms->useRow ? row_find_best(ms, ip, iLimit, offBasePtr) : hc_find_best(ms, ip, iLimit, offBasePtr);
 }
 
 /* ZSTD_compressBlock_lazy_generic :1516-1779; depth 0 = greedy, 1 = lazy, 2 = lazy2.  Returns the trailing literal run. */
 size_t zso_block_lazy(void* ssv, uint32_t rep[3], const uint8_t* src, size_t srcSize,
                       uint32_t* hashTable, uint8_t* tagTable, uint32_t* chainTable, unsigned hashLog, unsigned chainLog, unsigned searchLog,
-                      unsigned minMatch, unsigned depth) {     /* tagTable != NULL: row finder, else hash chain */
+                      unsigned minMatch, unsigned depth, int binaryTree) {     /* tagTable != NULL: row finder; else hash chain or binary tree */
     zso_seqStore* const ss = (zso_seqStore*)ssv;
     const uint8_t* const istart = src;
     const uint8_t* ip = istart;
@@ -196,7 +314,7 @@ size_t zso_block_lazy(void* ssv, uint32_t rep[3], const uint8_t* src, size_t src
     ms.rowLog = searchLog < 4 ? 4 : searchLog > 6 ? 6 : searchLog;
     ms.searchLog = searchLog; ms.rowHashLog = hashLog - ms.rowLog;
     ms.nextToUpdate = 2; ms.lazySkipping = 0;
-    ms.useRow = useRow; ms.chainTable = chainTable; ms.hashLog = hashLog; ms.chainLog = chainLog;
+    ms.useRow = binaryTree ? 2 : useRow; ms.chainTable = chainTable; ms.hashLog = hashLog; ms.chainLog = chainLog;
 
     ip += 1;                                            /* dictAndPrefixLength == 0 */
     {   uint32_t const maxRep = (uint32_t)(ip - prefixLowest);

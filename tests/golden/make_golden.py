@@ -61,7 +61,7 @@ def main():
         data = regenerate_input(spec)
         if len(data) <= 16384:
             continue
-        for level in (9, 6, 5):
+        for level in (9, 6, 5, 12):
             frame = ref_compress(data, level)
             assert not isinstance(frame, int)
             if len(frame) > 20000:
@@ -69,12 +69,12 @@ def main():
             fn = f"oneshot_{n:03d}_L{level}.zst"; n += 1
             (HERE / fn).write_bytes(frame)
             man["oneshot"].append({"file": fn, "level": level, "input": spec, "input_sha256": hashlib.sha256(data).hexdigest(), "frame_size": len(frame)})
-    # hash-chain finder: small inputs at levels 4 and 6
+    # hash-chain finder (levels 4, 6) and binary tree (level 9) on small inputs
     for spec in specs:
         data = regenerate_input(spec)
         if spec["kind"] != "corpus" or spec["size"] not in (1000, 5000, 16384):
             continue
-        for level in (4, 6):
+        for level in (4, 6, 9):
             frame = ref_compress(data, level)
             assert not isinstance(frame, int)
             fn = f"oneshot_{n:03d}_L{level}.zst"; n += 1

@@ -31,10 +31,10 @@ def _expected(data, level):
     return r
 
 
-@pytest.mark.parametrize("level", [3, 1, 4, 2, -1, 5, 7, 9])
+@pytest.mark.parametrize("level", [3, 1, 4, 2, -1, 5, 7, 9, 12])
 def test_compress_bit_exact_vs_oracle(ctx, level):
     todo = cases.special_cases() + cases.corpus_cases(32) + cases.edge_cases()
-    if level >= 9:
+    if level >= 11:
         todo = [t for t in todo if len(t[1]) > 16384]
     frames = ctx.compressBatch([d for _, d in todo], level)
     assert ctx.kernelLaunches() > 0
@@ -45,10 +45,10 @@ def test_compress_bit_exact_vs_oracle(ctx, level):
 def test_unsupported_levels_fail_loudly(ctx):
     from zstd_jni_b200.zstd import ZstdException
     with pytest.raises(ZstdException) as ei:
-        ctx.compressBatch([b"x" * 1000], 9)          # <= 16 KB at level 9: binary-tree finder, not built
+        ctx.compressBatch([b"x" * 1000], 11)         # <= 16 KB at level 11: btopt (optimal parser), not built
     assert ei.value.getErrorCode() == 40
     with pytest.raises(ZstdException) as ei:
-        ctx.compressBatch([b"x" * 100000], 12)       # btlazy2
+        ctx.compressBatch([b"x" * 100000], 13)       # btopt
     assert ei.value.getErrorCode() == 40
 
 

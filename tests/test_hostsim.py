@@ -14,12 +14,12 @@ from tests.oracle_util import (emu_compress, emu_decompress, hostsim_compress, h
 GOLDEN = Path(__file__).parent / "golden"
 
 
-@pytest.mark.parametrize("level", [3, 1, 4, 2, -1, -7, 5, 6, 9])
+@pytest.mark.parametrize("level", [3, 1, 4, 2, -1, -7, 5, 6, 9, 12])
 def test_hostsim_encoder_matches_oracle(level):
     todo = cases.special_cases() + cases.corpus_cases(16) + cases.edge_cases(classes=(0, 2, 4, 5, 7))
     if level >= 5:       # lazy levels (row match finder): keep the CPU suite short, the big inputs are what they are for
         todo = cases.special_cases() + cases.corpus_cases(8) + cases.edge_cases(classes=(0, 4), sizes=[7, 100, 1024, 5000, 16384, 16385, 65792, 100000, 131072])
-        if level >= 9:
+        if level >= 11:
             todo = [t for t in todo if len(t[1]) > 16384]
     for name, data in todo:
         exp = oracle_compress(data, level)

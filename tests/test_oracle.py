@@ -44,13 +44,13 @@ def test_committed_golden_vectors():
 
 
 @pytest.mark.skipif(ref() is None, reason="oracle/_ref not built (no reference sources here)")
-@pytest.mark.parametrize("level", [1, 2, 3, 4, -1, -5, 5, 6, 7, 9, 10])
+@pytest.mark.parametrize("level", [1, 2, 3, 4, -1, -5, 5, 6, 7, 9, 10, 12])
 def test_oracle_matches_compiled_reference(level):
     assert ref().ZSTD_versionString() == b"1.5.7"
     todo = cases.special_cases() + cases.corpus_cases(16) + cases.edge_cases(classes=(0, 4))
     for name, data in todo:
-        if level >= 9 and len(data) <= 16384:
-            assert oracle_compress(data, level) == -40     # <=16 KB table, level 9+: binary-tree finder, not restated
+        if level >= 11 and len(data) <= 16384:
+            assert oracle_compress(data, level) == -40     # <=16 KB table, level 11+: optimal parser (btopt), not restated
             continue
         exp = ref_compress(data, level)
         assert oracle_compress(data, level) == exp, (name, level)

@@ -23,35 +23,38 @@
 namespace zb {
 
 struct CParams { u32 windowLog, chainLog, hashLog, searchLog, minMatch, targetLength, strategy; };
-enum : u32 { S_fast = 1, S_dfast = 2, S_greedy = 3, S_lazy = 4, S_lazy2 = 5 };
+enum : u32 { S_fast = 1, S_dfast = 2, S_greedy = 3, S_lazy = 4, S_lazy2 = 5, S_btlazy2 = 6 };
 
 constexpr u32 MAX_SEQ = (BLOCKSIZE_MAX / 4) + 8;
-constexpr u32 ENC_HASHLOG_MAX = 17;     // largest hashLog / chainLog of the supported rows
+constexpr u32 ENC_HASHLOG_MAX = 18;     // largest hashLog / chainLog of the supported rows
 
 // ZSTD_getCParams_internal (:7759-7782) + ZSTD_adjustCParams_internal (:1472-1609) for a known
 // srcSize <= 128 KB, no dictionary.  Returns false when the level selects a parser this build lacks.
 ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize) {
-    // rows 0..10 of the "<=128 KB" table and 0..8 of the "<=16 KB" table (clevels.h:78-90,104-114).  greedy / lazy / lazy2
+    // rows 0..12 of the "<=128 KB" table and 0..10 of the "<=16 KB" table (clevels.h:78-92,104-116).  greedy / lazy / lazy2
     // run with the row-based match finder when windowLog > 14 (ZSTD_resolveRowMatchFinderMode, zstd_compress.c:238-245),
-    // i.e. for every srcSize > 16 KB, and with the hash-chain finder below; the binary-tree rows are not built.
-    const CParams t128[11] = { {17,12,12,1,5,1,S_fast}, {17,12,13,1,6,0,S_fast}, {17,13,15,1,5,0,S_fast}, {17,15,16,2,5,0,S_dfast}, {17,17,17,2,4,0,S_dfast},
+    // i.e. for every srcSize > 16 KB, and with the hash-chain finder below; btlazy2 uses the binary tree.  The rows from
+    // btopt on (optimal parser) are not built.
+    const CParams t128[13] = { {17,12,12,1,5,1,S_fast}, {17,12,13,1,6,0,S_fast}, {17,13,15,1,5,0,S_fast}, {17,15,16,2,5,0,S_dfast}, {17,17,17,2,4,0,S_dfast},
                                {17,16,17,3,4,2,S_greedy}, {17,16,17,3,4,4,S_lazy}, {17,16,17,3,4,8,S_lazy2}, {17,16,17,4,4,8,S_lazy2}, {17,16,17,5,4,8,S_lazy2},
-                               {17,16,17,6,4,8,S_lazy2} };
-    const CParams t16[9] = { {14,12,13,1,5,1,S_fast}, {14,14,15,1,5,0,S_fast}, {14,14,15,1,4,0,S_fast}, {14,14,15,2,4,0,S_dfast},
-                             {14,14,14,4,4,2,S_greedy}, {14,14,14,3,4,4,S_lazy}, {14,14,14,4,4,8,S_lazy2}, {14,14,14,6,4,8,S_lazy2}, {14,14,14,8,4,8,S_lazy2} };
+                               {17,16,17,6,4,8,S_lazy2}, {17,17,17,5,4,8,S_btlazy2}, {17,18,17,7,4,12,S_btlazy2} };
+    const CParams t16[11] = { {14,12,13,1,5,1,S_fast}, {14,14,15,1,5,0,S_fast}, {14,14,15,1,4,0,S_fast}, {14,14,15,2,4,0,S_dfast},
+                             {14,14,14,4,4,2,S_greedy}, {14,14,14,3,4,4,S_lazy}, {14,14,14,4,4,8,S_lazy2}, {14,14,14,6,4,8,S_lazy2}, {14,14,14,8,4,8,S_lazy2},
+                              {14,15,14,5,4,8,S_btlazy2}, {14,15,14,9,4,8,S_btlazy2} };
     if (srcSize > BLOCKSIZE_MAX) return false;
     int row = level;
     if (level == 0) row = 3;
     if (level < 0) row = 0;
     bool const small = srcSize <= 16 * 1024;
-    if (row > (small ? 8 : 10)) return false;
+    if (row > (small ? 10 : 12)) return false;
     CParams cp = small ? t16[row] : t128[row];
     if (level < 0) { int const l = level < -(1 << 17) ? -(1 << 17) : level; cp.targetLength = (u32)(-l); }
     u32 const tSize = (u32)srcSize;
     u32 const srcLog = (tSize < 64) ? 6 : highbit32(tSize - 1) + 1;
     if (cp.windowLog > srcLog) cp.windowLog = srcLog;
     if (cp.hashLog > cp.windowLog + 1) cp.hashLog = cp.windowLog + 1;
-    if (cp.chainLog > cp.windowLog) cp.chainLog = cp.windowLog;      // cycleLog == chainLog below btlazy2
+    {   u32 const cycleLog = cp.chainLog - (cp.strategy >= S_btlazy2 ? 1 : 0);      // ZSTD_cycleLog
+        if (cycleLog > cp.windowLog) cp.chainLog -= (cycleLog - cp.windowLog); }
     if (cp.windowLog < 10) cp.windowLog = 10;
     *out = cp;
     return true;
@@ -1452,7 +1455,8 @@ struct RowState {
     u32* hashTable; u8* tagTable; const u8* base;
     u32 hashCache[8];
     u32 rowHashLog, rowLog, searchLog, mls, nextToUpdate; bool lazySkipping;
-    bool useRow; u32* chainTable; u32 hashLog, chainLog;      // hash-chain finder (window <= 2^14)
+    u32 finder;                 // 0 = hash chain (window <= 2^14), 1 = row based, 2 = binary tree (btlazy2)
+    u32* chainTable; u32 hashLog, chainLog;
 };
 ZB_HD u32 row_hash(const u8* p, u32 hBits, u32 mls) {
     switch (mls) {
@@ -1575,10 +1579,107 @@ ZB_HDN size_t hc_find_best(RowState& ms, const u8* ip, const u8* iLimit, size_t*
     }
     return ml;
 }
-ZB_HD size_t lazy_find_best(RowState& ms, const u8* ip, const u8* iLimit, size_t* offBasePtr) {
-    return ms.useRow ? row_find_best(ms, ip, iLimit, offBasePtr) : hc_find_best(ms, ip, iLimit, offBasePtr);
+// Binary tree of the "dual unsorted" kind: ZSTD_BtFindBestMatch :399-408, ZSTD_updateDUBT :29-65, ZSTD_insertDUBT1 :74-163,
+// ZSTD_DUBT_findBestMatch :243-395 (noDict).  bt = W.hashSmall as pairs {smaller, larger}, btLog = chainLog - 1.
+ZB_HDN void dubt_insert1(RowState& ms, u32 curr, const u8* iend, u32 nbCompares, u32 btLow) {
+    u32* const bt = ms.chainTable;
+    u32 const btMask = (1u << (ms.chainLog - 1)) - 1;
+    size_t commonLengthSmaller = 0, commonLengthLarger = 0;
+    const u8* const ip = ms.base + curr;
+    u32* smallerPtr = bt + 2 * (curr & btMask);
+    u32* largerPtr = smallerPtr + 1;
+    u32 matchIndex = *smallerPtr;
+    u32 dummy32;
+    for (; nbCompares && (matchIndex > 2); --nbCompares) {
+        u32* const nextPtr = bt + 2 * (matchIndex & btMask);
+        size_t matchLength = commonLengthSmaller < commonLengthLarger ? commonLengthSmaller : commonLengthLarger;
+        const u8* const match = ms.base + matchIndex;
+        matchLength += count_match(ip + matchLength, match + matchLength, iend);
+        if (ip + matchLength == iend) break;
+        if (match[matchLength] < ip[matchLength]) {
+            *smallerPtr = matchIndex; commonLengthSmaller = matchLength;
+            if (matchIndex <= btLow) { smallerPtr = &dummy32; break; }
+            smallerPtr = nextPtr + 1; matchIndex = nextPtr[1];
+        } else {
+            *largerPtr = matchIndex; commonLengthLarger = matchLength;
+            if (matchIndex <= btLow) { largerPtr = &dummy32; break; }
+            largerPtr = nextPtr; matchIndex = nextPtr[0];
+        }
+    }
+    *smallerPtr = *largerPtr = 0;
 }
-ZB_HDN u32 parse_lazy(const EncWork& W, const u8* src, size_t srcSize, u32 hashLog, u32 chainLog, u32 searchLog, u32 minMatch, u32 depth, bool useRow, u32* lastLL) {
+ZB_HDN size_t bt_find_best(RowState& ms, const u8* ip, const u8* iend, size_t* offBasePtr) {
+    u32* const bt = ms.chainTable;
+    u32 const btMask = (1u << (ms.chainLog - 1)) - 1;
+    u32 const curr = (u32)(ip - ms.base);
+    u32 const windowLow = 2;
+    u32 const btLow = (btMask >= curr) ? 0 : curr - btMask;
+    u32 const unsortLimit = btLow > windowLow ? btLow : windowLow;
+    u32 nbCompares = 1u << ms.searchLog, nbCandidates = nbCompares, previousCandidate = 0;
+    if (ip < ms.base + ms.nextToUpdate) return 0;      // skipped area
+    for (u32 idx = ms.nextToUpdate; idx < curr; idx++) {      // ZSTD_updateDUBT
+        u32 const hh = row_hash(ms.base + idx, ms.hashLog, ms.mls);
+        u32* const nc = bt + 2 * (idx & btMask);
+        nc[0] = ms.hashTable[hh]; nc[1] = 1;          // ZSTD_DUBT_UNSORTED_MARK
+        ms.hashTable[hh] = idx;
+    }
+    ms.nextToUpdate = curr;
+    u32 const h = row_hash(ip, ms.hashLog, ms.mls);
+    u32 matchIndex = ms.hashTable[h];
+    u32* nextCandidate = bt + 2 * (matchIndex & btMask); u32* unsortedMark = nextCandidate + 1;
+    while ((matchIndex > unsortLimit) && (*unsortedMark == 1) && (nbCandidates > 1)) {
+        *unsortedMark = previousCandidate;
+        previousCandidate = matchIndex;
+        matchIndex = *nextCandidate;
+        nextCandidate = bt + 2 * (matchIndex & btMask); unsortedMark = nextCandidate + 1;
+        nbCandidates--;
+    }
+    if ((matchIndex > unsortLimit) && (*unsortedMark == 1)) *nextCandidate = *unsortedMark = 0;
+    matchIndex = previousCandidate;
+    while (matchIndex) {
+        u32 const nextCandidateIdx = bt[2 * (matchIndex & btMask) + 1];
+        dubt_insert1(ms, matchIndex, iend, nbCandidates, unsortLimit);
+        matchIndex = nextCandidateIdx;
+        nbCandidates++;
+    }
+    size_t commonLengthSmaller = 0, commonLengthLarger = 0, bestLength = 0;
+    u32* smallerPtr = bt + 2 * (curr & btMask);
+    u32* largerPtr = smallerPtr + 1;
+    u32 matchEndIdx = curr + 8 + 1;
+    u32 dummy32;
+    matchIndex = ms.hashTable[h];
+    ms.hashTable[h] = curr;
+    for (; nbCompares && (matchIndex > windowLow); --nbCompares) {
+        u32* const nextPtr = bt + 2 * (matchIndex & btMask);
+        size_t matchLength = commonLengthSmaller < commonLengthLarger ? commonLengthSmaller : commonLengthLarger;
+        const u8* const match = ms.base + matchIndex;
+        matchLength += count_match(ip + matchLength, match + matchLength, iend);
+        if (matchLength > bestLength) {
+            if (matchLength > matchEndIdx - matchIndex) matchEndIdx = matchIndex + (u32)matchLength;
+            if ((4 * (int)(matchLength - bestLength)) > (int)(highbit32(curr - matchIndex + 1) - highbit32((u32)*offBasePtr))) {
+                bestLength = matchLength; *offBasePtr = (size_t)(curr - matchIndex) + 3; }
+            if (ip + matchLength == iend) break;
+        }
+        if (match[matchLength] < ip[matchLength]) {
+            *smallerPtr = matchIndex; commonLengthSmaller = matchLength;
+            if (matchIndex <= btLow) { smallerPtr = &dummy32; break; }
+            smallerPtr = nextPtr + 1; matchIndex = nextPtr[1];
+        } else {
+            *largerPtr = matchIndex; commonLengthLarger = matchLength;
+            if (matchIndex <= btLow) { largerPtr = &dummy32; break; }
+            largerPtr = nextPtr; matchIndex = nextPtr[0];
+        }
+    }
+    *smallerPtr = *largerPtr = 0;
+    ms.nextToUpdate = matchEndIdx - 8;
+    return bestLength;
+}
+ZB_HD size_t lazy_find_best(RowState& ms, const u8* ip, const u8* iLimit, size_t* offBasePtr) {
+    if (ms.finder == 2) return bt_find_best(ms, ip, iLimit, offBasePtr);
+    return ms.finder == 1 ? row_find_best(ms, ip, iLimit, offBasePtr) : hc_find_best(ms, ip, iLimit, offBasePtr);
+}
+ZB_HDN u32 parse_lazy(const EncWork& W, const u8* src, size_t srcSize, u32 hashLog, u32 chainLog, u32 searchLog, u32 minMatch, u32 depth, u32 finder, u32* lastLL) {
+    bool const useRow = finder == 1;
     const u8* const istart = src;
     const u8* ip = istart;
     const u8* anchor = istart;
@@ -1587,7 +1688,7 @@ ZB_HDN u32 parse_lazy(const EncWork& W, const u8* src, size_t srcSize, u32 hashL
     const u8* const prefixLowest = src;
     u32 offset_1 = 1, offset_2 = 4, nbSeq = 0;
     RowState ms;
-    ms.useRow = useRow; ms.chainTable = W.hashSmall; ms.hashLog = hashLog; ms.chainLog = chainLog;
+    ms.finder = finder; ms.chainTable = W.hashSmall; ms.hashLog = hashLog; ms.chainLog = chainLog;
     ms.hashTable = W.hashLong; ms.tagTable = reinterpret_cast<u8*>(W.hashSmall); ms.base = src - 2;
     ms.mls = minMatch < 4 ? 4 : minMatch > 6 ? 6 : minMatch;
     ms.rowLog = searchLog < 4 ? 4 : searchLog > 6 ? 6 : searchLog;
@@ -1683,8 +1784,8 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
     {   // fresh tables: zero the used part (16-byte stores; the workspace is 16-byte aligned)
         u32 const nL = (1u << cp.hashLog) / 4;
         u32 const nS = (cp.strategy == S_dfast) ? (1u << cp.chainLog) / 4                               // short-hash table
-                     : (cp.strategy >= S_greedy) ? (cp.windowLog > 14 ? (1u << cp.hashLog) / 16          // tag bytes of the row finder
-                                                                        : (1u << cp.chainLog) / 4) : 0;  // chain table
+                     : (cp.strategy >= S_greedy) ? ((cp.strategy != S_btlazy2 && cp.windowLog > 14) ? (1u << cp.hashLog) / 16   // tag bytes of the row finder
+                                                                        : (1u << cp.chainLog) / 4) : 0;  // chain table / binary tree
         struct alignas(16) Q { u32 a, b, c, d; };
         Q* const qL = reinterpret_cast<Q*>(W.hashLong); Q* const qS = reinterpret_cast<Q*>(W.hashSmall);
         Q const z = { 0, 0, 0, 0 };
@@ -1698,7 +1799,8 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
         nbSeq = parse_fast_warp(w, W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
     } else {
         if (w.lane == 0) {
-            if (cp.strategy >= S_greedy) nbSeq = parse_lazy(W, src, srcSize, cp.hashLog, cp.chainLog, cp.searchLog, cp.minMatch, cp.strategy - S_greedy, cp.windowLog > 14, &lastLL);
+            if (cp.strategy >= S_greedy) nbSeq = parse_lazy(W, src, srcSize, cp.hashLog, cp.chainLog, cp.searchLog, cp.minMatch, cp.strategy == S_btlazy2 ? 2 : cp.strategy - S_greedy,
+                                                          cp.strategy == S_btlazy2 ? 2u : cp.windowLog > 14 ? 1u : 0u, &lastLL);
             else if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
             else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
         }
