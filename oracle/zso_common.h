@@ -82,6 +82,7 @@ uint32_t zso_OF_base(unsigned code);
 /* ---- public oracle API (oracle/zso.h mirrors this for ctypes users) ---- */
 size_t zso_compressBound(size_t srcSize);
 size_t zso_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level);
+size_t zso_compress_flags(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, unsigned flags);   /* 1 = checksum, 2 = no content size */
 size_t zso_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize);
 size_t zso_findFrameCompressedSize(const void* src, size_t srcSize);
 unsigned long long zso_getFrameContentSize(const void* src, size_t srcSize);

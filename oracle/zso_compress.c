@@ -872,25 +872,32 @@ size_t zso_block_lazy(void* ss, uint32_t rep[3], const uint8_t* src, size_t srcS
                       unsigned minMatch, unsigned depth, int binaryTree);
 
 /* ---------------------------------------------------------------- frame */
-size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t srcSize, int level) {
+uint64_t zso_xxh64(const void* data, size_t len, uint64_t seed);
+size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t srcSize, int level) { return zso_compress_flags(dstv, dstCapacity, srcv, srcSize, level, 0); }
+/* flags: 1 = ZSTD_c_checksumFlag on, 2 = ZSTD_c_contentSizeFlag off */
+size_t zso_compress_flags(void* dstv, size_t dstCapacity, const void* srcv, size_t srcSize, int level, unsigned flags) {
+    int const checksum = (flags & 1) != 0, contentSize = !(flags & 2);
+    uint32_t const sum = checksum ? (uint32_t)zso_xxh64(srcv, srcSize, 0) : 0; size_t const sumBytes = checksum ? 4 : 0;
     uint8_t* const dst = (uint8_t*)dstv; const uint8_t* const src = (const uint8_t*)srcv; zso_cparams cp; size_t pos = 0;
     if (zso_getCParams(&cp, level, srcSize)) return ZSO_ERROR(parameter_unsupported);
     /* supported block compressors: fast, dfast, greedy/lazy/lazy2 (row match finder when windowLog > 14,
      * ZSTD_resolveRowMatchFinderMode zstd_compress.c:238-245, else hash chain); the binary-tree finders are not restated */
     if (cp.strategy > ZSO_btlazy2) return ZSO_ERROR(parameter_unsupported);      /* btopt and up: optimal parser, not restated */
     if (dstCapacity < 18) return ZSO_ERROR(dstSize_tooSmall);   /* ZSTD_FRAMEHEADERSIZE_MAX :4716 */
-    /* ZSTD_writeFrameHeader :4695-4743 : contentSizeFlag=1, no checksum, no dictID; windowSize >= srcSize => singleSegment */
-    {   uint32_t const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256);
+    /* ZSTD_writeFrameHeader :4695-4743 : no dictID; the pledged size is known, so windowSize >= srcSize => singleSegment
+     * whenever the content size is written; otherwise the window descriptor byte appears instead */
+    {   uint32_t const fcsCode = contentSize ? (srcSize >= 256) + (srcSize >= 65536 + 256) : 0;
         zso_wr32(dst, 0xFD2FB528u); pos = 4;
-        dst[pos++] = (uint8_t)((1 << 5) + (fcsCode << 6));
-        switch (fcsCode) {
+        dst[pos++] = (uint8_t)((checksum ? 4 : 0) + (contentSize ? (1 << 5) : 0) + (fcsCode << 6));
+        if (!contentSize) dst[pos++] = (uint8_t)((cp.windowLog - 10) << 3);
+        else switch (fcsCode) {
         case 0: dst[pos++] = (uint8_t)srcSize; break;
         case 1: zso_wr16(dst + pos, (uint16_t)(srcSize - 256)); pos += 2; break;
         default: zso_wr32(dst + pos, (uint32_t)srcSize); pos += 4; break;
         } }
     if (srcSize == 0) {   /* ZSTD_writeEpilogue :5364-5372: one empty raw last block */
-        if (dstCapacity - pos < 3) return ZSO_ERROR(dstSize_tooSmall);
-        zso_wr24(dst + pos, 1); return pos + 3;
+        if (dstCapacity - pos < 3 + sumBytes) return ZSO_ERROR(dstSize_tooSmall);
+        zso_wr24(dst + pos, 1); if (checksum) zso_wr32(dst + pos + 3, sum); return pos + 3 + sumBytes;
     }
     {   size_t cSize = 0; uint8_t* const op = dst + pos; size_t const cap = dstCapacity - pos;
         if (cap < 3 + 2 + 1) return ZSO_ERROR(dstSize_tooSmall);   /* :4624-4626 */
@@ -927,9 +934,12 @@ size_t zso_compress(void* dstv, size_t dstCapacity, const void* srcv, size_t src
             if (srcSize + 3 > cap) return ZSO_ERROR(dstSize_tooSmall);
             zso_wr24(op, (uint32_t)(1 + (0 << 1) + (srcSize << 3)));
             memcpy(op + 3, src, srcSize);
-            return pos + 3 + srcSize;
+            cSize = srcSize;
+        } else zso_wr24(op, (uint32_t)(1 + (2 << 1) + (cSize << 3)));
+        if (checksum) {   /* ZSTD_writeEpilogue :5373-5378 */
+            if (cap - (3 + cSize) < 4) return ZSO_ERROR(dstSize_tooSmall);
+            zso_wr32(op + 3 + cSize, sum);
         }
-        zso_wr24(op, (uint32_t)(1 + (2 << 1) + (cSize << 3)));
-        return pos + 3 + cSize;
+        return pos + 3 + cSize + sumBytes;
     }
 }

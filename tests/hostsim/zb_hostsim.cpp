@@ -19,7 +19,9 @@ void zbh_parse_stats(unsigned long long* out, int reset) {
 }
 #endif
 
-size_t zbh_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level) {
+size_t zbh_compress_flags(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, unsigned flags);
+size_t zbh_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level) { return zbh_compress_flags(dst, dstCapacity, src, srcSize, level, 0); }
+size_t zbh_compress_flags(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, unsigned flags) {
     using namespace zb;
     if (srcSize > BLOCKSIZE_MAX) return ERR(E_srcSize_wrong);
     WarpHost w;
@@ -31,7 +33,7 @@ size_t zbh_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSi
     // inputs are read with aligned 8-byte loads: give the copy slack on both sides
     u8* in = (u8*)calloc(1, srcSize + 64);
     memcpy(in + 16, src, srcSize);
-    size_t r = compress_frame(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level);
+    size_t r = compress_frame(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level, flags);
     if (!isErr(r)) { if (r > dstCapacity) r = ERR(E_dstSize_tooSmall); else memcpy(dst, slot, r); }
     free(S); free(wk); free(slot); free(in);
     return r;

@@ -38,6 +38,7 @@ def _load(path, protos):
 def zso():
     L = _load(ZSO_PATH, [
         ("zso_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("zso_compress_flags", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint]),
         ("zso_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         ("zso_compressBound", C.c_size_t, [C.c_size_t]),
         ("zso_findFrameCompressedSize", C.c_size_t, [C.c_char_p, C.c_size_t]),
@@ -70,6 +71,7 @@ def ref():
 def hostsim():
     L = _load(HOSTSIM_PATH, [
         ("zbh_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("zbh_compress_flags", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint]),
         ("zbh_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         ("zbh_compress_bound", C.c_size_t, [C.c_size_t]),
         ("zbe_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
@@ -97,6 +99,37 @@ def _call_d(fn, frame: bytes, cap: int):
 def oracle_compress(data: bytes, level: int = 3):
     """Frame (bytes) or negative error code, from the plain-C restatement."""
     return _call_c(zso().zso_compress, data, level)
+
+
+def _call_flags(fn, data: bytes, level: int, flags: int):
+    cap = len(data) + (len(data) >> 8) + 1024
+    out = C.create_string_buffer(cap)
+    n = fn(out, cap, data, len(data), level, flags)
+    return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
+
+
+def oracle_compress_flags(data: bytes, level: int, checksum: bool = False, content_size: bool = True):
+    return _call_flags(zso().zso_compress_flags, data, level, (1 if checksum else 0) | (0 if content_size else 2))
+
+
+def hostsim_compress_flags(data: bytes, level: int, checksum: bool = False, content_size: bool = True):
+    return _call_flags(hostsim().zbh_compress_flags, data, level, (1 if checksum else 0) | (0 if content_size else 2))
+
+
+def ref_compress_flags(data: bytes, level: int, checksum: bool = False, content_size: bool = True):
+    """The compiled reference through ZSTD_CCtx_setParameter + ZSTD_compress2 (what J/ZstdCompressCtx drives)."""
+    R = ref()
+    cctx = R.ZSTD_createCCtx()
+    try:
+        R.ZSTD_CCtx_setParameter(cctx, 100, level)
+        R.ZSTD_CCtx_setParameter(cctx, 201, 1 if checksum else 0)
+        R.ZSTD_CCtx_setParameter(cctx, 200, 1 if content_size else 0)
+        cap = len(data) + (len(data) >> 8) + 1024
+        out = C.create_string_buffer(cap)
+        n = R.ZSTD_compress2(cctx, out, cap, data, len(data))
+        return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
+    finally:
+        R.ZSTD_freeCCtx(cctx)
 
 
 def oracle_decompress(frame: bytes, cap: int):

@@ -54,14 +54,27 @@ def test_manual_buffers_and_too_small_dst():                # Zstd.scala:38-53,1
             c.compressByteArray(buf, 100, 10 ** 6, data, 0, len(data))
 
 
+def test_checksum_and_content_size_flags():                 # J/ZstdCompressCtx.setChecksum / setContentSize (N/jni_fast_zstd.c:277-318)
+    from zstd_jni_b200.zstd import Zstd, ZstdCompressCtx
+    from tests.oracle_util import oracle_compress_flags
+    for data in _inputs():
+        for checksum, content_size in ((True, True), (False, False), (True, False)):
+            with ZstdCompressCtx() as c:
+                c.setLevel(3).setChecksum(checksum).setContentSize(content_size)
+                z = c.compress(data)
+            assert z == oracle_compress_flags(data, 3, checksum, content_size), (len(data), checksum, content_size)
+            assert Zstd.decompress(z, len(data)) == data
+            assert (Zstd.getFrameContentSize(z) == len(data)) == content_size or len(data) == 0
+    bad = bytearray(z); bad[-1] ^= 0x40                      # corrupt the stored checksum of the last frame
+    from zstd_jni_b200.zstd import ZstdException
+    with pytest.raises(ZstdException) as ei:
+        Zstd.decompress(bytes(bad), len(data))
+    assert ei.value.getErrorCode() == 22                     # checksum_wrong
+
+
 def test_unsupported_parameters_are_reported():
     from zstd_jni_b200.zstd import ZstdCompressCtx, ZstdException
     data = _inputs()[3]
-    with ZstdCompressCtx() as c:
-        c.setLevel(3).setChecksum(True)
-        with pytest.raises(ZstdException) as ei:
-            c.compress(data)
-        assert ei.value.getErrorCode() == 40
     with ZstdCompressCtx() as c:
         c.setLevel(19)
         with pytest.raises(ZstdException) as ei:

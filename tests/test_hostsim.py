@@ -27,6 +27,17 @@ def test_hostsim_encoder_matches_oracle(level):
         assert got == exp, (name, level, exp if isinstance(exp, int) else len(exp), got if isinstance(got, int) else len(got))
 
 
+@pytest.mark.parametrize("checksum,content_size", [(True, True), (False, False), (True, False)])
+def test_hostsim_frame_flags_match_oracle(checksum, content_size):
+    from tests.oracle_util import hostsim_compress_flags, oracle_compress_flags
+    for name, data in cases.special_cases()[:3] + cases.corpus_cases(4) + cases.edge_cases(classes=(0,), sizes=[0, 1, 7, 255, 256, 1000, 65791, 65792, 131072]):
+        for level in (3, 6):
+            exp = oracle_compress_flags(data, level, checksum, content_size)
+            assert hostsim_compress_flags(data, level, checksum, content_size) == exp, (name, level)
+            if not isinstance(exp, int):
+                assert hostsim_decompress(exp, len(data)) == data
+
+
 def test_hostsim_decoder_on_golden_fixtures():
     man = json.loads((GOLDEN / "manifest.json").read_text())
     from tests.golden.make_golden import regenerate_input

@@ -58,6 +58,20 @@ def test_oracle_matches_compiled_reference(level):
 
 
 @pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("checksum,content_size", [(True, True), (False, False), (True, False)])
+def test_oracle_frame_flags_match_reference(checksum, content_size):
+    """ZSTD_c_checksumFlag / ZSTD_c_contentSizeFlag as J/ZstdCompressCtx.setChecksum / setContentSize set them."""
+    from tests.oracle_util import oracle_compress_flags, ref_compress_flags
+    for name, data in cases.special_cases()[:4] + cases.corpus_cases(6) + cases.edge_cases(classes=(0, 4), sizes=[0, 1, 7, 255, 256, 1000, 65791, 65792, 131072]):
+        for level in (3, 1, 9):
+            if level == 9 and 0 < len(data) <= 16384 and False:
+                continue
+            exp = ref_compress_flags(data, level, checksum, content_size)
+            assert oracle_compress_flags(data, level, checksum, content_size) == exp, (name, level)
+            assert oracle_decompress(exp, len(data)) == data
+
+
+@pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
 def test_oracle_decodes_reference_streams():
     """multi-block frames with cross-block matches, repeat modes, checksums (what ZstdOutputStream emits)."""
     from zstd_jni_b200 import corpus

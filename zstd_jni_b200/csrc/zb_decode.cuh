@@ -549,28 +549,6 @@ ZB_HDN size_t decode_block(const C& w, DecShared& S, const u8* frameStart, u8* o
     return (size_t)(op - op0);
 }
 
-// ---------------------------------------------------------------- XXH64
-// published xxHash64 (N/common/xxhash.h), serial; only used when the frame asks for it.
-ZB_HD u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
-ZB_HDN u64 xxh64(const u8* p, size_t len) {
-    constexpr u64 P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
-    const u8* const end = p + len; u64 h;
-    auto rnd = [&](u64 acc, u64 in) { acc += in * P2; acc = rotl64(acc, 31); return acc * P1; };
-    auto mrg = [&](u64 acc, u64 v) { v = rnd(0, v); acc ^= v; return acc * P1 + P4; };
-    if (len >= 32) {
-        u64 v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
-        do { v1 = rnd(v1, load64(p)); v2 = rnd(v2, load64(p + 8)); v3 = rnd(v3, load64(p + 16)); v4 = rnd(v4, load64(p + 24)); p += 32; } while (p + 32 <= end);
-        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
-        h = mrg(h, v1); h = mrg(h, v2); h = mrg(h, v3); h = mrg(h, v4);
-    } else h = P5;
-    h += (u64)len;
-    while (p + 8 <= end) { h ^= rnd(0, load64_n(p, 8)); h = rotl64(h, 27) * P1 + P4; p += 8; }
-    if (p + 4 <= end) { h ^= (u64)load32(p) * P1; h = rotl64(h, 23) * P2 + P3; p += 4; }
-    while (p < end) { h ^= (*p++) * P5; h = rotl64(h, 11) * P1; }
-    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
-    return h;
-}
-
 // ------------------------------------------------------------ frame layer
 struct FrameHeader { u32 headerSize; u64 contentSize; u64 windowSize; u32 blockSizeMax; u32 checksum, skippable, skipLen, hasContentSize; };
 

@@ -1773,6 +1773,7 @@ ZB_HDN u32 parse_lazy(const EncWork& W, const u8* src, size_t srcSize, u32 hashL
 //   parse_stage   match finding -> sequences (W.seq*), their count and the trailing literal run
 //   encode_stage  frame/block headers, literal gathering, Huffman + FSE entropy stage
 // Together they emit what ZSTD_compress2 would with dstCapacity = ZSTD_compressBound(srcSize).
+constexpr u32 FRAME_CHECKSUM = 1, FRAME_NO_CONTENT_SIZE = 2;      // frameFlags: ZSTD_c_checksumFlag = 1, ZSTD_c_contentSizeFlag = 0
 constexpr u32 PARSE_SKIPPED = 0xFFFFFFFFu;     // nbSeq marker: srcSize < 7, the block is stored raw (ZSTD_buildSeqStore :3273-3280)
 
 template <class C>
@@ -1813,25 +1814,35 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
 
 // `dst` must have room for compress_bound(srcSize) + 32 bytes.  Uniform return value.
 template <class C>
-ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level, u32 nbSeq, u32 lastLL) {
+ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level, u32 nbSeq, u32 lastLL,
+                           u32 frameFlags = 0) {
     CParams cp;
     if (!get_cparams(&cp, level, srcSize)) return ERR(E_parameter_unsupported);
     if (dstCapacity < 18) return ERR(E_dstSize_tooSmall);
     size_t pos = 0;
-    u32 const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256);
-    if (w.lane == 0) {   // ZSTD_writeFrameHeader :4695-4743
+    // ZSTD_writeFrameHeader :4695-4743 (no dictionary): the pledged size is known in a one-shot call, so the window
+    // covers the input and the frame is "single segment" whenever the content size is written
+    bool const checksum = (frameFlags & FRAME_CHECKSUM) != 0, contentSize = !(frameFlags & FRAME_NO_CONTENT_SIZE);
+    u32 const fcsCode = contentSize ? (srcSize >= 256) + (srcSize >= 65536 + 256) : 0;
+    if (w.lane == 0) {
         dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
-        dst[4] = (u8)((1 << 5) + (fcsCode << 6));
-        if (fcsCode == 0) dst[5] = (u8)srcSize;
+        dst[4] = (u8)((checksum ? 4 : 0) + (contentSize ? (1 << 5) : 0) + (fcsCode << 6));
+        if (!contentSize) dst[5] = (u8)((cp.windowLog - 10) << 3);
+        else if (fcsCode == 0) dst[5] = (u8)srcSize;
         else if (fcsCode == 1) { u32 const v = (u32)srcSize - 256; dst[5] = (u8)v; dst[6] = (u8)(v >> 8); }
         else { u32 const v = (u32)srcSize; dst[5] = (u8)v; dst[6] = (u8)(v >> 8); dst[7] = (u8)(v >> 16); dst[8] = (u8)(v >> 24); }
     }
-    pos = 5 + (fcsCode == 0 ? 1 : fcsCode == 1 ? 2 : 4);
-    if (srcSize == 0) {   // ZSTD_writeEpilogue :5364-5372
-        if (dstCapacity - pos < 3) return ERR(E_dstSize_tooSmall);
-        if (w.lane == 0) { dst[pos] = 1; dst[pos + 1] = 0; dst[pos + 2] = 0; }
+    pos = 5 + (!contentSize ? 1 : fcsCode == 0 ? 1 : fcsCode == 1 ? 2 : 4);
+    // ZSTD_writeEpilogue :5344-5381: the low 32 bits of XXH64(content) follow the last block when asked for
+    u32 const sumBytes = checksum ? 4 : 0;
+    u32 sum = 0;
+    if (checksum && w.lane == 0) sum = (u32)xxh64(src, srcSize);
+    if (srcSize == 0) {   // :5364-5372
+        if (dstCapacity - pos < 3 + sumBytes) return ERR(E_dstSize_tooSmall);
+        if (w.lane == 0) { dst[pos] = 1; dst[pos + 1] = 0; dst[pos + 2] = 0;
+                           if (checksum) { dst[pos + 3] = (u8)sum; dst[pos + 4] = (u8)(sum >> 8); dst[pos + 5] = (u8)(sum >> 16); dst[pos + 6] = (u8)(sum >> 24); } }
         w.sync();
-        return pos + 3;
+        return pos + 3 + sumBytes;
     }
     u8* const op = dst + pos; size_t const cap = dstCapacity - pos;
     if (cap < 3 + 2 + 1) return ERR(E_dstSize_tooSmall);
@@ -1870,21 +1881,23 @@ ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, 
         if (srcSize + 3 > cap) return ERR(E_dstSize_tooSmall);
         if (w.lane == 0) { u32 const h = 1 + (u32)(srcSize << 3); op[0] = (u8)h; op[1] = (u8)(h >> 8); op[2] = (u8)(h >> 16); }
         for (size_t i = (size_t)w.lane; i < srcSize; i += C::W) op[3 + i] = src[i];
-        w.sync();
-        return pos + 3 + srcSize;
+        cSize = srcSize;
+    } else if (w.lane == 0) { u32 const h = 1 + (2 << 1) + (u32)(cSize << 3); op[0] = (u8)h; op[1] = (u8)(h >> 8); op[2] = (u8)(h >> 16); }
+    if (checksum) {
+        if (cap - (3 + cSize) < 4) return ERR(E_dstSize_tooSmall);
+        if (w.lane == 0) { u8* const q = op + 3 + cSize; q[0] = (u8)sum; q[1] = (u8)(sum >> 8); q[2] = (u8)(sum >> 16); q[3] = (u8)(sum >> 24); }
     }
-    if (w.lane == 0) { u32 const h = 1 + (2 << 1) + (u32)(cSize << 3); op[0] = (u8)h; op[1] = (u8)(h >> 8); op[2] = (u8)(h >> 16); }
     w.sync();
-    return pos + 3 + cSize;
+    return pos + 3 + cSize + sumBytes;
 }
 
 // both stages on one context (host instantiation, single-kernel use)
 template <class C>
-ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level) {
+ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level, u32 frameFlags = 0) {
     u32 nbSeq = 0, lastLL = 0;
     size_t const r = parse_stage(w, W, src, srcSize, level, &nbSeq, &lastLL);
     if (isErr(r)) return r;
-    return encode_stage(w, S, W, dst, dstCapacity, src, srcSize, level, nbSeq, lastLL);
+    return encode_stage(w, S, W, dst, dstCapacity, src, srcSize, level, nbSeq, lastLL, frameFlags);
 }
 
 }  // namespace zb
