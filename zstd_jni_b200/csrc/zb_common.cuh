@@ -308,6 +308,18 @@ static const InvProbTable h_invprob = ZB_INVPROB_INIT;
 #define ZB_INVPROB (::zb::h_invprob.v)
 #endif
 
+// ---- optional per-phase cycle counters (profiling builds only: -DZB_PHASE_TIMERS; scripts/gpu_phases.sh)
+#if defined(ZB_PHASE_TIMERS) && defined(__CUDACC__)
+__device__ unsigned long long g_phaseCycles[16];
+#endif
+#if defined(ZB_PHASE_TIMERS) && defined(__CUDA_ARCH__)
+#define ZB_PT_DECL long long zb_pt0 = clock64();
+#define ZB_PT(k) do { long long const zb_t = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&::zb::g_phaseCycles[k], (unsigned long long)(zb_t - zb_pt0)); zb_pt0 = zb_t; } while (0)
+#else
+#define ZB_PT_DECL
+#define ZB_PT(k) do {} while (0)
+#endif
+
 // ---- warp contexts
 #if defined(__CUDACC__)
 // LANES consecutive lanes of a hardware warp acting as one cooperative group (LANES = 32: the whole warp).

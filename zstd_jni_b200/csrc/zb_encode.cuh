@@ -951,6 +951,7 @@ ZB_HDN size_t lit_rle(const C& w, u8* dst, const u8* src, size_t n) {
 template <class C>
 ZB_HDN size_t compress_literals(const C& w, EncShared& S, u8* dst, size_t cap, const u8* src, size_t n, u32 strategy, bool disableLitCompression, bool suspectUncompressible) {
     size_t const lhSize = 3 + (n >= 1024) + (n >= 16384); bool const single = n < 256;
+    ZB_PT_DECL
     if (disableLitCompression) return lit_raw(w, dst, cap, src, n);
     {   int const sh = (9 - (int)strategy) < 3 ? (9 - (int)strategy) : 3;
         if (n < ((size_t)8 << sh)) return lit_raw(w, dst, cap, src, n); }
@@ -967,6 +968,7 @@ ZB_HDN size_t compress_literals(const C& w, EncShared& S, u8* dst, size_t cap, c
         }
         u32 maxSV = 255;
         u32 const largest = hist_warp(w, S.count, &maxSV, src, n);
+        ZB_PT(7);      // literal histogram
         if (largest == n) { if (w.lane == 0) o[0] = src[0]; cLit = 1; break; }
         if (largest <= (n >> 7) + 4) break;
         // tree + table description on lane 0
@@ -978,6 +980,7 @@ ZB_HDN size_t compress_literals(const C& w, EncShared& S, u8* dst, size_t cap, c
         }
         w.sync();
         hSize = w.bcast(hSize);
+        ZB_PT(8);      // Huffman tree + table description (lane 0)
         if (isErr(hSize)) { cLit = hSize; break; }
         if (hSize + 12ul >= n) break;
         u8* op = o + hSize; size_t const opcap = ocap - hSize;
@@ -1018,6 +1021,7 @@ ZB_HDN size_t compress_literals(const C& w, EncShared& S, u8* dst, size_t cap, c
         cLit = total;
     } while (0);
     w.sync();
+    ZB_PT(9);          // Huffman streams
     {   size_t const minGain = (n >> 6) + 2;
         if (cLit == 0 || isErr(cLit) || cLit >= n - minGain) return lit_raw(w, dst, cap, src, n); }
     if (cLit == 1) {
@@ -1094,10 +1098,12 @@ ZB_HDN u32 select_encoding_cost(EncShared& S, u32 max, size_t mostFrequent, size
 template <class C>
 ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t cap, u32 nbSeq, size_t litSize, u32 strategy, bool disableLitCompression) {
     u8* op = dst; u8* const oend = dst + cap;
+    ZB_PT_DECL
     {   bool const suspect = (nbSeq == 0) || (litSize / nbSeq >= 20);
         size_t const c = compress_literals(w, S, op, cap, W.lit, litSize, strategy, disableLitCompression, suspect);
         if (isErr(c)) return c;
         op += c; }
+    ZB_PT(6);          // literals in total (= phases 7..9 + fallbacks)
     if ((oend - op) < 3 + 1) return ERR(E_dstSize_tooSmall);
     if (w.lane == 0) {
         if (nbSeq < 128) op[0] = (u8)nbSeq;
@@ -1113,6 +1119,7 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
         mlc[u] = (u8)ml_code(W.seqML[u] - MINMATCH);
     }
     w.sync();
+    ZB_PT(2);          // seqToCodes
     u8* const seqHead = op++;
     size_t lastCountSize = 0; u32 types[3];
     // ZSTD_buildSequencesStatistics :2762-2880 : histogram on all lanes, table work on lane 0
@@ -1164,6 +1171,7 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
     //  2. all lanes pack the per-sequence bit groups (state bits OF,ML,LL then extra bits LL,ML,OF) at
     //     offsets from a prefix sum, the last lane appends the final states (ML,OF,LL) and the end mark.
     if (w.lane == 0) *seqHead = (u8)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
+    ZB_PT(3);          // sequence statistics + tables
     size_t streamSize = 0;
     {
         u16* const stb = W.stbits;
@@ -1197,6 +1205,7 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
             S.tmp[t] = state;
         }
         w.sync();
+        ZB_PT(4);      // FSE state chains
         u32 const B = (nbSeq + C::W - 1) / C::W;
         u32 const j0 = (u32)w.lane * B < nbSeq ? (u32)w.lane * B : nbSeq;
         u32 const j1 = j0 + B < nbSeq ? j0 + B : nbSeq;
@@ -1235,6 +1244,7 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
         lb.close(w);
         w.sync();
     }
+    ZB_PT(5);          // sequence bit packing
     op += streamSize;
     if (lastCountSize && (lastCountSize + streamSize) < 4) return 0;    // :2992-2998
     return (size_t)(op - dst);
@@ -1845,6 +1855,7 @@ ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, 
         return pos + 3 + sumBytes;
     }
     u8* const op = dst + pos; size_t const cap = dstCapacity - pos;
+    ZB_PT_DECL
     if (cap < 3 + 2 + 1) return ERR(E_dstSize_tooSmall);
     size_t cSize = 0;
     if (nbSeq != PARSE_SKIPPED) {
@@ -1870,6 +1881,7 @@ ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, 
             for (u32 j = (u32)w.lane; j < lastLL; j += C::W) W.lit[litSize + j] = src[sp + j];
             litSize += lastLL;
             w.sync(); }
+        ZB_PT(1);      // literal gather
         bool const disableLit = (cp.strategy == S_fast && cp.targetLength > 0);   // ZSTD_literalsCompressionIsDisabled
         cSize = entropy_compress(w, S, W, op + 3, cap - 3, nbSeq, litSize, cp.strategy, disableLit);
         // ZSTD_entropyCompressSeqStore_wExtLitBuffer :3005-3042
