@@ -46,7 +46,12 @@ typedef enum {
     ZSTD_c_contentSizeFlag = 200,
     ZSTD_c_checksumFlag = 201,
     ZSTD_c_dictIDFlag = 202,
-    ZSTD_c_nbWorkers = 400
+    ZSTD_c_nbWorkers = 400,
+    /* extension of this library (not in libzstd): when non-zero, ZSTD_compress2 / ZSTD_compressCCtx accept inputs larger
+     * than one block and write them as one independent frame per 128 KB -- a legal zstd stream (every decoder reads
+     * concatenated frames) but NOT the bytes the reference would produce.  Off by default: without it such inputs are
+     * refused with ZSTD_error_parameter_unsupported.  Environment default: ZSTDB200_MULTIFRAME=1. */
+    ZSTDB200_c_multiFrame = 0xB200
 } ZSTD_cParameter;
 typedef enum { ZSTD_reset_session_only = 1, ZSTD_reset_parameters = 2, ZSTD_reset_session_and_parameters = 3 } ZSTD_ResetDirective;
 typedef enum { ZSTD_e_continue = 0, ZSTD_e_flush = 1, ZSTD_e_end = 2 } ZSTD_EndDirective;

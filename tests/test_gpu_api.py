@@ -72,6 +72,21 @@ def test_checksum_and_content_size_flags():                 # J/ZstdCompressCtx.
     assert ei.value.getErrorCode() == 22                     # checksum_wrong
 
 
+def test_multi_frame_extension_for_large_inputs():
+    """> 128 KB is refused by default (no approximation of multi-block frames); ZSTDB200_c_multiFrame opts into one frame per 128 KB."""
+    from zstd_jni_b200 import corpus
+    from zstd_jni_b200.zstd import Zstd, ZstdCompressCtx
+    from tests.oracle_util import oracle_compress, oracle_decompress
+    data = b"".join(corpus.chunk(i).tobytes() for i in (0, 1, 5))[: 300000]
+    with ZstdCompressCtx() as c:
+        c.setLevel(3).setMultiFrame(True)
+        z = c.compress(data)
+    exp = b"".join(oracle_compress(data[o:o + 131072], 3) for o in range(0, len(data), 131072))
+    assert z == exp                                          # every 128 KB piece is the reference's frame for that piece
+    assert Zstd.decompress(z, len(data)) == data
+    assert oracle_decompress(z, len(data)) == data           # any zstd decoder reads concatenated frames
+
+
 def test_unsupported_parameters_are_reported():
     from zstd_jni_b200.zstd import ZstdCompressCtx, ZstdException
     data = _inputs()[3]

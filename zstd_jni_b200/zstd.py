@@ -181,6 +181,11 @@ class ZstdCompressCtx(_AutoClose):
     def setLevel(self, level: int):                      # :69-75
         return self._set(ZSTD_c_compressionLevel, level)
 
+    def setMultiFrame(self, flag: bool):
+        """Extension (ZSTDB200_c_multiFrame): inputs > 128 KB become one independent frame per 128 KB instead of an error.
+        The result is a legal zstd stream but not the reference's bytes."""
+        return self._set(0xB200, int(flag))
+
     def setChecksum(self, flag: bool):
         return self._set(ZSTD_c_checksumFlag, int(flag))
 
