@@ -1778,6 +1778,178 @@ ZB_HDN u32 parse_lazy(const EncWork& W, const u8* src, size_t srcSize, u32 hashL
     return nbSeq;
 }
 
+// ---- warp-cooperative row search (levels 5..10 on inputs > 16 KB).  The lazy control flow stays sequential and is
+// executed uniformly by all lanes (same scalars, broadcast loads); what is spread over the lanes is the search itself:
+// lane j takes the j-th entry of the row in the reference's visiting order (head, head+1, ... mod rowEntries), the tag
+// compare becomes one ballot, every accepted candidate is measured by its own lane, and the winner is the first
+// candidate of maximal length -- which is what the serial loop's "strictly longer replaces" rule selects.  Table
+// writes are made by lane 0 only.
+template <class C>
+ZB_HD void row_update_warp(const C& w, RowState& ms, const u8* ip) {
+    u32 idx = ms.nextToUpdate;
+    u32 const target = (u32)(ip - ms.base);
+    u32 const rowMask = (1u << ms.rowLog) - 1;
+    auto insert_range = [&](u32 from, u32 to) {
+        for (u32 i = from; i < to; ++i) {
+            u32 const hash = row_next_cached(ms, i);           // uniform: keeps every lane's cache identical
+            if (w.lane == 0) {
+                u32 const relRow = (hash >> 8) << ms.rowLog;
+                u8* const tagRow = ms.tagTable + relRow;
+                u32 const pos = row_next_index(tagRow, rowMask);
+                tagRow[pos] = (u8)hash;
+                ms.hashTable[relRow + pos] = i;
+            }
+        }
+    };
+    if (target - idx > 384) {
+        insert_range(idx, idx + 96);
+        idx = target - 32;
+        row_fill_cache(ms, idx, ip + 1);
+    }
+    insert_range(idx, target);
+    ms.nextToUpdate = target;
+}
+template <class C>
+ZB_HDN size_t row_find_best_warp(const C& w, RowState& ms, const u8* ip, const u8* iLimit, size_t* offBasePtr) {
+    u32 const curr = (u32)(ip - ms.base);
+    u32 const lowLimit = 2;
+    u32 const rowEntries = 1u << ms.rowLog, rowMask = rowEntries - 1;
+    u32 const maxAttempts = 1u << (ms.searchLog < ms.rowLog ? ms.searchLog : ms.rowLog);
+    u32 hash;
+    if (!ms.lazySkipping) { row_update_warp(w, ms, ip); hash = row_next_cached(ms, curr); }
+    else { hash = row_hash(ip, ms.rowHashLog + 8, ms.mls); ms.nextToUpdate = curr; }
+    w.sync();                                              // lane 0's insertions are visible to everybody
+    u32 const relRow = (hash >> 8) << ms.rowLog;
+    u32 const tag = hash & 0xFF;
+    u32* const row = ms.hashTable + relRow;
+    u8* const tagRow = ms.tagTable + relRow;
+    u32 const head = *tagRow & rowMask;
+    u32 const ip4 = load32(ip);
+    u32 bestLen = 0, bestIdx = 0; bool stopped = false; u32 used = 0;
+    for (u32 base = 0; base < rowEntries && !stopped && used < maxAttempts; base += (u32)C::W) {
+        u32 const j = base + (u32)w.lane;
+        u32 const matchPos = (head + j) & rowMask;
+        bool const hit = j < rowEntries && matchPos != 0 && tagRow[matchPos] == (u8)tag;
+        u32 const idx = hit ? row[matchPos] : 0;
+        u32 const hitMask = w.ballot(hit), staleMask = w.ballot(hit && idx < lowLimit);
+        u32 valid = hitMask;
+        if (staleMask) { valid &= (1u << ctz32(staleMask)) - 1; stopped = true; }
+        u32 const rank = used + popc32(valid & ((1u << w.lane) - 1));
+        bool const mine = ((valid >> w.lane) & 1) && rank < maxAttempts;
+        u32 len = 0;
+        if (mine) { const u8* const match = ms.base + idx; if (load32(match) == ip4) len = (u32)count_match(ip, match, iLimit); }
+        u32 const lmax = w.max(len);
+        if (lmax > bestLen && lmax >= 4) {                 // strictly longer than everything before: first lane holding it wins
+            u32 const who = ctz32(w.ballot(mine && len == lmax));
+            bestLen = lmax; bestIdx = w.shfl(idx, (int)who);
+        }
+        used += popc32(valid);
+    }
+    w.sync();
+    if (w.lane == 0) {                                     // "insert current byte into hashtable too"
+        u32 const pos = row_next_index(tagRow, rowMask);
+        tagRow[pos] = (u8)tag;
+        row[pos] = ms.nextToUpdate;
+    }
+    ms.nextToUpdate++;
+    w.sync();
+    if (bestLen >= 4) { *offBasePtr = (size_t)(curr - bestIdx) + 3; return bestLen; }
+    return 3;
+}
+template <class C>
+ZB_HDN u32 parse_lazy_warp(const C& w, const EncWork& W, const u8* src, size_t srcSize, u32 hashLog, u32 searchLog, u32 minMatch, u32 depth, u32* lastLL) {
+    bool const useRow = true; u32 const finder = 1, chainLog = 0;
+    const u8* const istart = src;
+    const u8* ip = istart;
+    const u8* anchor = istart;
+    const u8* const iend = istart + srcSize;
+    const u8* const ilimit = useRow ? iend - 8 - 8 : iend - 8;
+    const u8* const prefixLowest = src;
+    u32 offset_1 = 1, offset_2 = 4, nbSeq = 0;
+    RowState ms;
+    ms.finder = finder; ms.chainTable = W.hashSmall; ms.hashLog = hashLog; ms.chainLog = chainLog;
+    ms.hashTable = W.hashLong; ms.tagTable = reinterpret_cast<u8*>(W.hashSmall); ms.base = src - 2;
+    ms.mls = minMatch < 4 ? 4 : minMatch > 6 ? 6 : minMatch;
+    ms.rowLog = searchLog < 4 ? 4 : searchLog > 6 ? 6 : searchLog;
+    ms.searchLog = searchLog; ms.rowHashLog = hashLog - ms.rowLog;
+    ms.nextToUpdate = 2; ms.lazySkipping = false;
+    ip += 1;
+    {   u32 const maxRep = (u32)(ip - prefixLowest);
+        if (offset_2 > maxRep) offset_2 = 0;
+        if (offset_1 > maxRep) offset_1 = 0; }
+    if (useRow) row_fill_cache(ms, ms.nextToUpdate, ilimit);
+    while (ip < ilimit) {
+        size_t matchLength = 0;
+        size_t offBase = 1;
+        const u8* start = ip + 1;
+        bool store = false;
+        if ((offset_1 > 0) && (load32(ip + 1 - offset_1) == load32(ip + 1))) {
+            matchLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
+            if (depth == 0) store = true;
+        }
+        if (!store) {
+            {   size_t offbaseFound = 999999999;
+                size_t const ml2 = row_find_best_warp(w, ms, ip, iend, &offbaseFound);
+                if (ml2 > matchLength) { matchLength = ml2; start = ip; offBase = offbaseFound; } }
+            if (matchLength < 4) {
+                size_t const step = ((size_t)(ip - anchor) >> 8) + 1;      // kSearchStrength
+                ip += step;
+                ms.lazySkipping = step > 8;                                // kLazySkippingStep
+                continue;
+            }
+            if (depth >= 1)
+            while (ip < ilimit) {
+                ip++;
+                if ((offBase) && ((offset_1 > 0) && (load32(ip) == load32(ip - offset_1)))) {
+                    size_t const mlRep = count_match(ip + 4, ip + 4 - offset_1, iend) + 4;
+                    int const gain2 = (int)(mlRep * 3);
+                    int const gain1 = (int)(matchLength * 3 - highbit32((u32)offBase) + 1);
+                    if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
+                }
+                {   size_t ofbCandidate = 999999999;
+                    size_t const ml2 = row_find_best_warp(w, ms, ip, iend, &ofbCandidate);
+                    int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofbCandidate));
+                    int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 4);
+                    if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; } }
+                if ((depth == 2) && (ip < ilimit)) {
+                    ip++;
+                    if ((offBase) && ((offset_1 > 0) && (load32(ip) == load32(ip - offset_1)))) {
+                        size_t const mlRep = count_match(ip + 4, ip + 4 - offset_1, iend) + 4;
+                        int const gain2 = (int)(mlRep * 4);
+                        int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 1);
+                        if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
+                    }
+                    {   size_t ofbCandidate = 999999999;
+                        size_t const ml2 = row_find_best_warp(w, ms, ip, iend, &ofbCandidate);
+                        int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofbCandidate));
+                        int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 7);
+                        if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; } }
+                }
+                break;
+            }
+            if (offBase > 3) {   // catch up
+                size_t const off = offBase - 3;
+                while (((start > anchor) && (start - off > prefixLowest)) && (start[-1] == (start - off)[-1])) { start--; matchLength++; }
+                offset_2 = offset_1; offset_1 = (u32)off;
+            }
+        }
+        if (w.lane == 0) { W.seqLL[nbSeq] = (u32)(start - anchor); W.seqOF[nbSeq] = (u32)offBase; W.seqML[nbSeq] = (u32)matchLength; }
+        nbSeq++;
+        anchor = ip = start + matchLength;
+        if (ms.lazySkipping) { if (useRow) row_fill_cache(ms, ms.nextToUpdate, ilimit); ms.lazySkipping = false; }
+        while (((ip <= ilimit) && (offset_2 > 0)) && (load32(ip) == load32(ip - offset_2))) {
+            matchLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
+            u32 const tmp = offset_2; offset_2 = offset_1; offset_1 = tmp;
+            if (w.lane == 0) { W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = (u32)matchLength; }
+            nbSeq++;
+            ip += matchLength; anchor = ip;
+        }
+    }
+    w.sync();
+    *lastLL = (u32)(iend - anchor);
+    return nbSeq;
+}
+
 // ------------------------------------------------------------------ frame
 // A chunk becomes a frame in two stages that may run in different kernels (and with different group widths):
 //   parse_stage   match finding -> sequences (W.seq*), their count and the trailing literal run
@@ -1808,6 +1980,8 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
         nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
     } else if (C::W > 1 && cp.strategy == S_fast) {
         nbSeq = parse_fast_warp(w, W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
+    } else if (C::W > 1 && cp.strategy >= S_greedy && cp.strategy <= S_lazy2 && cp.windowLog > 14) {
+        nbSeq = parse_lazy_warp(w, W, src, srcSize, cp.hashLog, cp.searchLog, cp.minMatch, cp.strategy - S_greedy, &lastLL);
     } else {
         if (w.lane == 0) {
             if (cp.strategy >= S_greedy) nbSeq = parse_lazy(W, src, srcSize, cp.hashLog, cp.chainLog, cp.searchLog, cp.minMatch, cp.strategy == S_btlazy2 ? 2 : cp.strategy - S_greedy,
