@@ -1482,13 +1482,22 @@ ZB_HD u32 row_next_index(u8* tagRow, u32 rowMask) {
     *tagRow = (u8)next;
     return next;
 }
+// The hash cache is the reference's latency trick (ZSTD_row_prefetch :816-829): the row of position idx + 8 is
+// requested while position idx is searched.  Same here, towards L2: tag row (<= 64 B) and index row (<= 256 B).
+ZB_HD void row_prefetch(const RowState& ms, u32 hash) {
+    u32 const relRow = (hash >> 8) << ms.rowLog;
+    prefetch_l2(ms.tagTable + relRow);
+    prefetch_l2(ms.hashTable + relRow);
+    if (ms.rowLog == 6) prefetch_l2(ms.hashTable + relRow + 32);
+}
 ZB_HD void row_fill_cache(RowState& ms, u32 idx, const u8* iLimit) {
     u32 const maxElems = (ms.base + idx) > iLimit ? 0 : (u32)(iLimit - (ms.base + idx) + 1);
     u32 const lim = idx + (8 < maxElems ? 8 : maxElems);
-    for (; idx < lim; ++idx) ms.hashCache[idx & 7] = row_hash(ms.base + idx, ms.rowHashLog + 8, ms.mls);
+    for (; idx < lim; ++idx) { u32 const h = row_hash(ms.base + idx, ms.rowHashLog + 8, ms.mls); row_prefetch(ms, h); ms.hashCache[idx & 7] = h; }
 }
 ZB_HD u32 row_next_cached(RowState& ms, u32 idx) {
     u32 const newHash = row_hash(ms.base + idx + 8, ms.rowHashLog + 8, ms.mls);
+    row_prefetch(ms, newHash);
     u32 const hash = ms.hashCache[idx & 7];
     ms.hashCache[idx & 7] = newHash;
     return hash;
