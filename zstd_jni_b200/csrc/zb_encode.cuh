@@ -1,22 +1,28 @@
 // zb_encode.cuh -- warp-cooperative one-shot Zstandard frame encoder for inputs of at
 // most one block (<= 128 KB): the unit of work of the batch API.  The emitted frame is
-// byte-identical to the reference's ZSTD_compress2(chunk, level) (levels whose
-// parameters select the dfast or fast parser at these sizes, i.e. 1..4 and negatives).
+// byte-identical to the reference's ZSTD_compress2(chunk, level) for the negative levels and
+// levels 1..12 (1..10 on inputs <= 16 KB), i.e. every strategy below the optimal parser.
 //
 // Reference decisions being reproduced (N/ = luben/zstd-jni src/main/native/):
 //   parameters     N/compress/clevels.h:78-130, N/compress/zstd_compress.c:1472-1609,7759-7782
 //   framing        N/compress/zstd_compress.c:4591-4743,5344-5381
-//   parsers        N/compress/zstd_double_fast.c:105-323 (dfast), N/compress/zstd_fast.c:190-423 (fast)
+//   parsers        N/compress/zstd_double_fast.c:105-323 (dfast), N/compress/zstd_fast.c:190-423 (fast),
+//                  N/compress/zstd_lazy.c:1516-1779 (greedy/lazy/lazy2/btlazy2) with the row-based (:775-1283),
+//                  hash-chain (:620-733) and binary-tree (:22-408) match finders
 //   literals       N/compress/zstd_compress_literals.c:129-235, N/compress/huf_compress.c:146-1434, N/compress/hist.c
-//   sequences      N/compress/zstd_compress.c:2693-3042, N/compress/zstd_compress_sequences.c:156-382,
+//   sequences      N/compress/zstd_compress.c:2693-3042, N/compress/zstd_compress_sequences.c:17-382,
 //                  N/compress/fse_compress.c:68-525
 //
 // GPU mapping (W = 32 lanes, one warp per frame):
-//   * the greedy parse is inherently sequential (every table write feeds later reads), so lane 0
-//     walks the block; hash tables live in a per-warp global workspace that stays L2-resident;
-//   * literal gathering, histograms, code computation, Huffman stream sizing run on all lanes;
-//   * Huffman tree / FSE normalisation / table descriptions are tiny scalar jobs on lane 0 in shared memory;
-//   * the four Huffman streams are emitted by lanes 0..3 at offsets known from the sizing pass.
+//   * dfast / fast: a batch of consecutive search positions is probed by consecutive lanes; pending table writes are
+//     forwarded between lanes (__match_any_sync), the first event in the reference's order ends the batch and only
+//     what the serial code would have written is committed (parse_dfast_warp, parse_fast_warp);
+//   * lazy family with the row finder: sequential control flow executed uniformly, the row search spread over the
+//     lanes (parse_lazy_warp); hash-chain and binary-tree finders run on lane 0;
+//   * literal gathering, histograms, code computation, bit packing of the Huffman and sequence streams run on all
+//     lanes (lane slices + exclusive-scan bit offsets); Huffman tree / FSE normalisation / table descriptions are
+//     scalar jobs on lane 0 in shared memory; the three FSE state chains run on lanes 0..2;
+//   * the serial variants (parse_dfast, parse_fast, parse_lazy) are the 1-lane host instantiation used by the tests.
 #pragma once
 #include "zb_common.cuh"
 
