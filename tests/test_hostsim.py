@@ -121,3 +121,42 @@ def test_staged_batch_decoder_matches_oracle(emu):
             for cap in (len(data), len(data) - 7):
                 a = oracle_decompress(bytes(zz), cap); b = staged_decompress(bytes(zz), cap, emu)
                 assert a == b, (idx, k, cap, a if isinstance(a, int) else "ok", b if isinstance(b, int) else "ok")
+
+
+def test_randomised_levels_and_sizes():
+    """Seeded fuzz over every supported level and input shape: kernel source (1 lane and 32-lane emulator) == oracle
+    (== compiled reference when it is available)."""
+    import numpy as np
+    from zstd_jni_b200 import corpus
+    from tests.oracle_util import ref_compress
+    rng = np.random.default_rng(4242)
+
+    def make(kind, n):
+        if kind == 0:
+            return corpus.chunk(int(rng.integers(0, 64))).tobytes()[:n]
+        if kind == 1:
+            a = np.resize(rng.integers(0, 256, int(rng.integers(3, 300)), dtype=np.uint8), n).copy()
+            k = int(n * rng.random() * 0.05)
+            if k:
+                a[rng.integers(0, n, k)] = rng.integers(0, 256, k, dtype=np.uint8)
+            return a.tobytes()
+        if kind == 2:
+            return rng.integers(0, int(rng.integers(2, 40)), n, dtype=np.uint8).tobytes()
+        parts, left = [], n
+        while left > 0:
+            ln = min(left, int(rng.integers(1, 20000)))
+            parts.append(make(int(rng.integers(0, 3)), ln)); left -= ln
+        return b"".join(parts)
+
+    levels = [-7, -1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12]
+    for it in range(48):
+        n = int(rng.choice([rng.integers(0, 300), rng.integers(300, 16385), rng.integers(16385, 131073), 131072]))
+        data = make(int(rng.integers(0, 4)), n)
+        level = int(rng.choice(levels))
+        exp = oracle_compress(data, level)
+        if level >= 11 and n <= 16384:
+            assert exp == -40
+        elif ref() is not None:
+            assert exp == ref_compress(data, level), (it, n, level)
+        got = hostsim_compress(data, level) if it % 2 == 0 else emu_compress(data, level)
+        assert got == exp, (it, n, level)
