@@ -356,6 +356,7 @@ struct GroupDev {
         return x - v;
     }
     // OR one byte into memory shared with neighbouring lanes (32-bit atomic on the containing word)
+    __device__ __forceinline__ void atomic_or32(u32* p, u32 v) const { atomicOr(p, v); }
     __device__ __forceinline__ void atomic_or_byte(u8* p, u32 v) const {
         uintptr_t const a = reinterpret_cast<uintptr_t>(p);
         atomicOr(reinterpret_cast<unsigned int*>(a & ~(uintptr_t)3), v << (8 * (u32)(a & 3)));
@@ -376,6 +377,7 @@ struct WarpHost {
     u32 max(u32 v) const { return v; }
     void atomic_inc(u32* p) const { ++*p; }
     u32 exscan(u32) const { return 0; }
+    void atomic_or32(u32* p, u32 v) const { *p |= v; }
     void atomic_or_byte(u8* p, u32 v) const { *p = (u8)(*p | v); }
 };
 

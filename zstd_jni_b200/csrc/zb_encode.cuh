@@ -1212,42 +1212,71 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
         }
         w.sync();
         ZB_PT(4);      // FSE state chains
-        u32 const B = (nbSeq + C::W - 1) / C::W;
-        u32 const j0 = (u32)w.lane * B < nbSeq ? (u32)w.lane * B : nbSeq;
-        u32 const j1 = j0 + B < nbSeq ? j0 + B : nbSeq;
+        // 2. bit packing, one row of C::W sequences at a time (lane = sequence, so every global access is coalesced; per-lane
+        //    slices of the nine arrays used to thrash L1): bit offsets inside the row come from an exclusive scan, the
+        //    fields are OR-ed into a shared-memory row buffer, whole bytes are flushed with coalesced stores and the
+        //    partial last byte is carried into the next row.
         u32 mine = 0;
-        for (u32 j = j0; j < j1; j++) {
+        for (u32 j = (u32)w.lane; j < nbSeq; j += C::W) {        // sizing pass
             u32 const n = nbSeq - 1 - j;
             mine += ZB_T.LL_bits[llc[n]] + ZB_T.ML_bits[mlc[n]] + ofc[n];
             if (j) mine += (stb[n] >> 12) + (stb[MAX_SEQ + n] >> 12) + (stb[2 * MAX_SEQ + n] >> 12);
         }
-        u32 const start = w.exscan(mine);
-        u32 const seqBits = w.bcast(start + mine, C::W - 1);
+        u32 const seqBits = w.sum(mine);
         size_t const totalBits = (size_t)seqBits + S.ctab(0).tableLog + S.ctab(1).tableLog + S.ctab(2).tableLog + 1;
         size_t const capLeft = (size_t)(oend - op);
         if (capLeft <= 8 || (totalBits >> 3) >= capLeft - 8) return ERR(E_dstSize_tooSmall);
         streamSize = (totalBits + 7) >> 3;
-        for (size_t i = (size_t)w.lane; i < streamSize; i += C::W) op[i] = 0;
-        w.sync();
-        LaneBits<C> lb; lb.init(op, start);
-        for (u32 j = j0; j < j1; j++) {
-            u32 const n = nbSeq - 1 - j;
-            if (j) {
-                u32 const o = stb[MAX_SEQ + n], m = stb[2 * MAX_SEQ + n], l = stb[n];
-                lb.add(w, o & 0xFFF, o >> 12); lb.add(w, m & 0xFFF, m >> 12); lb.add(w, l & 0xFFF, l >> 12);
+        u32* const rowBuf = S.count;                     // the histogram is free now; a row needs at most (W * 90 + 7) bits
+        const u8* const rowBytes = reinterpret_cast<const u8*>(rowBuf);
+        u32 carryBits = 0, carryVal = 0; size_t outPos = 0;
+        auto or_bits = [&](u32 pos, u32 v, u32 bits) {
+            if (!bits) return;
+            w.atomic_or32(&rowBuf[pos >> 5], v << (pos & 31));
+            if ((pos & 31) + bits > 32) w.atomic_or32(&rowBuf[(pos >> 5) + 1], v >> (32 - (pos & 31)));
+        };
+        for (u32 base = 0; base < nbSeq; base += C::W) {
+            u32 const j = base + (u32)w.lane; bool const valid = j < nbSeq;
+            u32 const n = valid ? nbSeq - 1 - j : 0;
+            u32 fo = 0, fm = 0, fl = 0, lbits = 0, mbits = 0, obits = 0, vl = 0, vm = 0, vo = 0;
+            if (valid) {
+                if (j) { fo = stb[MAX_SEQ + n]; fm = stb[2 * MAX_SEQ + n]; fl = stb[n]; }
+                lbits = ZB_T.LL_bits[llc[n]]; mbits = ZB_T.ML_bits[mlc[n]]; obits = ofc[n];
+                vl = W.seqLL[n] & ((1u << lbits) - 1);
+                vm = (W.seqML[n] - MINMATCH) & ((1u << mbits) - 1);
+                vo = W.seqOF[n] & (obits >= 32 ? 0xFFFFFFFFu : ((1u << obits) - 1));
             }
-            u32 const lbits = ZB_T.LL_bits[llc[n]], mbits = ZB_T.ML_bits[mlc[n]], obits = ofc[n];
-            lb.add(w, W.seqLL[n] & ((1u << lbits) - 1), lbits);
-            lb.add(w, (W.seqML[n] - MINMATCH) & ((1u << mbits) - 1), mbits);
-            lb.add(w, W.seqOF[n] & (obits >= 32 ? 0xFFFFFFFFu : ((1u << obits) - 1)), obits);
+            u32 const myBits = (fo >> 12) + (fm >> 12) + (fl >> 12) + lbits + mbits + obits;
+            u32 const pre = w.exscan(myBits);
+            u32 const rowBits = w.bcast(pre + myBits, C::W - 1) + carryBits;
+            u32 const nWords = (rowBits + 31) >> 5;
+            for (u32 i = (u32)w.lane; i <= nWords; i += C::W) rowBuf[i] = i ? 0 : carryVal;
+            w.sync();
+            if (valid) {
+                u32 pos = pre + carryBits;
+                or_bits(pos, fo & 0xFFF, fo >> 12); pos += fo >> 12;
+                or_bits(pos, fm & 0xFFF, fm >> 12); pos += fm >> 12;
+                or_bits(pos, fl & 0xFFF, fl >> 12); pos += fl >> 12;
+                or_bits(pos, vl, lbits); pos += lbits;
+                or_bits(pos, vm, mbits); pos += mbits;
+                or_bits(pos, vo, obits);
+            }
+            w.sync();
+            u32 const nBytes = rowBits >> 3;
+            for (u32 i = (u32)w.lane; i < nBytes; i += C::W) op[outPos + i] = rowBytes[i];
+            carryBits = rowBits & 7;
+            carryVal = carryBits ? (u32)rowBytes[nBytes] & ((1u << carryBits) - 1) : 0;
+            outPos += nBytes;
+            w.sync();
         }
-        if (w.lane == C::W - 1) {
-            lb.add(w, S.tmp[2] & ((1u << S.ctab(2).tableLog) - 1), S.ctab(2).tableLog);
-            lb.add(w, S.tmp[1] & ((1u << S.ctab(1).tableLog) - 1), S.ctab(1).tableLog);
-            lb.add(w, S.tmp[0] & ((1u << S.ctab(0).tableLog) - 1), S.ctab(0).tableLog);
-            lb.add(w, 1, 1);
+        if (w.lane == 0) {      // final states (ML, OF, LL), the end mark, and whatever the last row left over
+            u64 acc = carryVal; u32 nb = carryBits;
+            acc |= (u64)(S.tmp[2] & ((1u << S.ctab(2).tableLog) - 1)) << nb; nb += S.ctab(2).tableLog;
+            acc |= (u64)(S.tmp[1] & ((1u << S.ctab(1).tableLog) - 1)) << nb; nb += S.ctab(1).tableLog;
+            acc |= (u64)(S.tmp[0] & ((1u << S.ctab(0).tableLog) - 1)) << nb; nb += S.ctab(0).tableLog;
+            acc |= (u64)1 << nb; nb += 1;
+            for (u32 i = 0; i * 8 < nb; i++) op[outPos + i] = (u8)(acc >> (8 * i));
         }
-        lb.close(w);
         w.sync();
     }
     ZB_PT(5);          // sequence bit packing
