@@ -36,24 +36,36 @@ constexpr u32 ENC_HASHLOG_MAX = 18;     // largest hashLog / chainLog of the sup
 
 // ZSTD_getCParams_internal (:7759-7782) + ZSTD_adjustCParams_internal (:1472-1609) for a known
 // srcSize <= 128 KB, no dictionary.  Returns false when the level selects a parser this build lacks.
+// Level tables (clevels.h:78-92,104-116) in constant memory on the device, as a plain static on the host.
+struct LevelTables { CParams t128[13]; CParams t16[11]; };
+#define ZB_LEVEL_TABLES_INIT { { {17,12,12,1,5,1,S_fast}, {17,12,13,1,6,0,S_fast}, {17,13,15,1,5,0,S_fast}, {17,15,16,2,5,0,S_dfast}, {17,17,17,2,4,0,S_dfast}, \
+                               {17,16,17,3,4,2,S_greedy}, {17,16,17,3,4,4,S_lazy}, {17,16,17,3,4,8,S_lazy2}, {17,16,17,4,4,8,S_lazy2}, {17,16,17,5,4,8,S_lazy2}, \
+                               {17,16,17,6,4,8,S_lazy2}, {17,17,17,5,4,8,S_btlazy2}, {17,18,17,7,4,12,S_btlazy2} }, \
+                               { {14,12,13,1,5,1,S_fast}, {14,14,15,1,5,0,S_fast}, {14,14,15,1,4,0,S_fast}, {14,14,15,2,4,0,S_dfast}, \
+                             {14,14,14,4,4,2,S_greedy}, {14,14,14,3,4,4,S_lazy}, {14,14,14,4,4,8,S_lazy2}, {14,14,14,6,4,8,S_lazy2}, {14,14,14,8,4,8,S_lazy2}, \
+                              {14,15,14,5,4,8,S_btlazy2}, {14,15,14,9,4,8,S_btlazy2} } }
+#if defined(__CUDACC__)
+static __constant__ LevelTables c_levels = ZB_LEVEL_TABLES_INIT;
+#endif
+static const LevelTables h_levels = ZB_LEVEL_TABLES_INIT;
+#if defined(__CUDA_ARCH__)
+#define ZB_LEVELS (::zb::c_levels)
+#else
+#define ZB_LEVELS (::zb::h_levels)
+#endif
+
 ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize) {
     // rows 0..12 of the "<=128 KB" table and 0..10 of the "<=16 KB" table (clevels.h:78-92,104-116).  greedy / lazy / lazy2
     // run with the row-based match finder when windowLog > 14 (ZSTD_resolveRowMatchFinderMode, zstd_compress.c:238-245),
     // i.e. for every srcSize > 16 KB, and with the hash-chain finder below; btlazy2 uses the binary tree.  The rows from
     // btopt on (optimal parser) are not built.
-    const CParams t128[13] = { {17,12,12,1,5,1,S_fast}, {17,12,13,1,6,0,S_fast}, {17,13,15,1,5,0,S_fast}, {17,15,16,2,5,0,S_dfast}, {17,17,17,2,4,0,S_dfast},
-                               {17,16,17,3,4,2,S_greedy}, {17,16,17,3,4,4,S_lazy}, {17,16,17,3,4,8,S_lazy2}, {17,16,17,4,4,8,S_lazy2}, {17,16,17,5,4,8,S_lazy2},
-                               {17,16,17,6,4,8,S_lazy2}, {17,17,17,5,4,8,S_btlazy2}, {17,18,17,7,4,12,S_btlazy2} };
-    const CParams t16[11] = { {14,12,13,1,5,1,S_fast}, {14,14,15,1,5,0,S_fast}, {14,14,15,1,4,0,S_fast}, {14,14,15,2,4,0,S_dfast},
-                             {14,14,14,4,4,2,S_greedy}, {14,14,14,3,4,4,S_lazy}, {14,14,14,4,4,8,S_lazy2}, {14,14,14,6,4,8,S_lazy2}, {14,14,14,8,4,8,S_lazy2},
-                              {14,15,14,5,4,8,S_btlazy2}, {14,15,14,9,4,8,S_btlazy2} };
     if (srcSize > BLOCKSIZE_MAX) return false;
     int row = level;
     if (level == 0) row = 3;
     if (level < 0) row = 0;
     bool const small = srcSize <= 16 * 1024;
     if (row > (small ? 10 : 12)) return false;
-    CParams cp = small ? t16[row] : t128[row];
+    CParams cp = small ? ZB_LEVELS.t16[row] : ZB_LEVELS.t128[row];
     if (level < 0) { int const l = level < -(1 << 17) ? -(1 << 17) : level; cp.targetLength = (u32)(-l); }
     u32 const tSize = (u32)srcSize;
     u32 const srcLog = (tSize < 64) ? 6 : highbit32(tSize - 1) + 1;
@@ -69,12 +81,16 @@ ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize) {
 ZB_HD size_t compress_bound(size_t n) { return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0); }
 
 // ---- per-warp global workspace (carved by the host, see zb_capi.cu)
+// One sequence as the parsers hand it to the entropy stage: 16 bytes, so that storing it is a single request (three
+// 4-byte stores to three arrays were 14 % of the write requests of the parse kernel) and a row of sequences is read with
+// one 16-byte load per lane.
+struct alignas(16) Seq { u32 ll, of, ml, pad; };      // litLength, offBase, matchLength
 struct EncWork {
     u32* hashLong;      // 1 << ENC_HASHLOG_MAX entries, zeroed by the kernel per frame (only the used part)
     u32* hashSmall;     // 1 << ENC_HASHLOG_MAX entries
-    u32* seqLL;         // MAX_SEQ each
-    u32* seqOF;
-    u32* seqML;
+    Seq* seq;           // MAX_SEQ records
+    ZB_HD void put(u32 i, u32 ll, u32 of, u32 ml) const { Seq q; q.ll = ll; q.of = of; q.ml = ml; q.pad = 0; seq[i] = q; }
+    ZB_HD Seq get(u32 i) const { return seq[i]; }
     u8* lit;            // BLOCKSIZE_MAX + 32
     u8* codes;          // 3 * MAX_SEQ
     u16* stbits;        // 3 * MAX_SEQ : per sequence and stream, FSE state bits (value | nbBits << 12)
@@ -87,15 +103,13 @@ ZB_HD void enc_entropy_work_carve(EncWork& w, u8* base) {
     w.stbits = reinterpret_cast<u16*>(base);
 }
 ZB_HD size_t enc_work_bytes() {
-    return (size_t)2 * (4u << ENC_HASHLOG_MAX) + (size_t)3 * 4 * MAX_SEQ + enc_entropy_work_bytes() + 64;
+    return (size_t)2 * (4u << ENC_HASHLOG_MAX) + (size_t)16 * MAX_SEQ + enc_entropy_work_bytes() + 64;
 }
 ZB_HD EncWork enc_work_carve(u8* base) {
     EncWork w;
     w.hashLong = reinterpret_cast<u32*>(base); base += (size_t)4 << ENC_HASHLOG_MAX;
     w.hashSmall = reinterpret_cast<u32*>(base); base += (size_t)4 << ENC_HASHLOG_MAX;
-    w.seqLL = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
-    w.seqOF = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
-    w.seqML = reinterpret_cast<u32*>(base); base += 4 * (size_t)MAX_SEQ;
+    w.seq = reinterpret_cast<Seq*>(base); base += 16 * (size_t)MAX_SEQ;
     enc_entropy_work_carve(w, base);
     return w;
 }
@@ -193,7 +207,7 @@ ZB_HDN u32 parse_dfast(const EncWork& W, const u8* src, size_t srcSize, u32 hBit
         if (kind == 1) {
             mLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
             ip++;
-            W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = mLength; nbSeq++;
+            W.put(nbSeq, (u32)(ip - anchor), 1, mLength); nbSeq++;
         } else {
             if (kind == 2) {
                 match = base + idxl0;
@@ -211,7 +225,7 @@ ZB_HDN u32 parse_dfast(const EncWork& W, const u8* src, size_t srcSize, u32 hBit
             while (((ip > anchor) & (match > prefixLowest)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
             offset_2 = offset_1; offset_1 = offset;
             if (step < 4) hashLong[hl1] = (u32)(ip1 - base);
-            W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = offset + 3; W.seqML[nbSeq] = mLength; nbSeq++;
+            W.put(nbSeq, (u32)(ip - anchor), offset + 3, mLength); nbSeq++;
         }
         ip += mLength; anchor = ip;
         if (ip <= ilimit) {
@@ -225,7 +239,7 @@ ZB_HDN u32 parse_dfast(const EncWork& W, const u8* src, size_t srcSize, u32 hBit
                 u32 const t = offset_2; offset_2 = offset_1; offset_1 = t;
                 hashSmall[hash_ptr(ip, hBitsS, mls)] = (u32)(ip - base);
                 hashLong[hash_ptr(ip, hBitsL, 8)] = (u32)(ip - base);
-                W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength; nbSeq++;
+                W.put(nbSeq, 0, 1, rLength); nbSeq++;
                 ip += rLength; anchor = ip;
             }
         }
@@ -331,7 +345,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             while (rep2Pending && (ip <= ilimit) && (off2 > 0) && (load32(src + ip) == load32(src + ip - (int)off2))) {
                 u32 const rLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)ip + 4 - off2) + 4;
                 u32 const t = off2; off2 = off1; off1 = t;
-                if (lane == 0) { W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength; }   // table writes are never read again
+                if (lane == 0) { W.put(nbSeq, 0, 1, rLength); }   // table writes are never read again
                 nbSeq++; ip += (int)rLength; anchor = ip;
             }
             break;
@@ -405,7 +419,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
         if (kinde == 4) {   // immediate repcode at ip (lane 0): :308-320; its table writes were lane 0's commits
             u32 const rLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)ip + 4 - off2) + 4;
             u32 const t = off2; off2 = off1; off1 = t;
-            if (lane == 0) { W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength; }
+            if (lane == 0) { W.put(nbSeq, 0, 1, rLength); }
             nbSeq++; ip += (int)rLength; anchor = ip;
             rep2Pending = true;
             continue;
@@ -423,7 +437,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
         if (kinde == 1) {
             ip = pe + 1;
             mLength = wcount(w, src, (u32)n, (u32)ip + 4, (u32)ip + 4 - off1) + 4;
-            if (lane == 0) { W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = mLength; }
+            if (lane == 0) { W.put(nbSeq, (u32)(ip - anchor), 1, mLength); }
             nbSeq++;
         } else {
             ip = pe;
@@ -447,7 +461,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             off2 = off1; off1 = offset;
             if (lane == 0) {
                 if (ste < 4) hashLong[hl1] = cell((u32)p1e + 2, tag8(d81));
-                W.seqLL[nbSeq] = (u32)(ip - anchor); W.seqOF[nbSeq] = offset + 3; W.seqML[nbSeq] = mLength;
+                W.put(nbSeq, (u32)(ip - anchor), offset + 3, mLength);
             }
             nbSeq++;
         }
@@ -1126,9 +1140,10 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
     if (nbSeq == 0) { w.sync(); return (size_t)(op - dst); }
     u8* const llc = W.codes; u8* const ofc = llc + MAX_SEQ; u8* const mlc = ofc + MAX_SEQ;
     for (u32 u = (u32)w.lane; u < nbSeq; u += C::W) {     // ZSTD_seqToCodes :2693-2719
-        llc[u] = (u8)ll_code(W.seqLL[u]);
-        ofc[u] = (u8)highbit32(W.seqOF[u]);
-        mlc[u] = (u8)ml_code(W.seqML[u] - MINMATCH);
+        Seq const q = W.get(u);
+        llc[u] = (u8)ll_code(q.ll);
+        ofc[u] = (u8)highbit32(q.of);
+        mlc[u] = (u8)ml_code(q.ml - MINMATCH);
     }
     w.sync();
     ZB_PT(2);          // seqToCodes
@@ -1248,9 +1263,10 @@ ZB_HDN size_t entropy_compress(const C& w, EncShared& S, const EncWork& W, u8* d
             if (valid) {
                 if (j) { fo = stb[MAX_SEQ + n]; fm = stb[2 * MAX_SEQ + n]; fl = stb[n]; }
                 lbits = ZB_T.LL_bits[llc[n]]; mbits = ZB_T.ML_bits[mlc[n]]; obits = ofc[n];
-                vl = W.seqLL[n] & ((1u << lbits) - 1);
-                vm = (W.seqML[n] - MINMATCH) & ((1u << mbits) - 1);
-                vo = W.seqOF[n] & (obits >= 32 ? 0xFFFFFFFFu : ((1u << obits) - 1));
+                Seq const q = W.get(n);
+                vl = q.ll & ((1u << lbits) - 1);
+                vm = (q.ml - MINMATCH) & ((1u << mbits) - 1);
+                vo = q.of & (obits >= 32 ? 0xFFFFFFFFu : ((1u << obits) - 1));
             }
             u32 const myBits = (fo >> 12) + (fm >> 12) + (fl >> 12) + lbits + mbits + obits;
             u32 const pre = w.exscan(myBits);
@@ -1346,7 +1362,7 @@ ZB_HDN u32 parse_fast(const EncWork& W, const u8* src, size_t srcSize, u32 hlog,
             while (((ip0 > anchor) & (match0 > prefixStart)) && (ip0[-1] == match0[-1])) { ip0--; match0--; mLength++; }
         }
         mLength += count_match(ip0 + mLength, match0 + mLength, iend);
-        W.seqLL[nbSeq] = (u32)(ip0 - anchor); W.seqOF[nbSeq] = offcode; W.seqML[nbSeq] = mLength; nbSeq++;
+        W.put(nbSeq, (u32)(ip0 - anchor), offcode, mLength); nbSeq++;
         ip0 += mLength; anchor = ip0;
         if (ip0 <= ilimit) {
             hashTable[hash_ptr(base + current0 + 2, hlog, mls)] = current0 + 2;
@@ -1357,7 +1373,7 @@ ZB_HDN u32 parse_fast(const EncWork& W, const u8* src, size_t srcSize, u32 hlog,
                     { u32 const t = rep2; rep2 = rep1; rep1 = t; }
                     hashTable[hash_ptr(ip0, hlog, mls)] = (u32)(ip0 - base);
                     ip0 += rLength;
-                    W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength; nbSeq++;
+                    W.put(nbSeq, 0, 1, rLength); nbSeq++;
                     anchor = ip0;
                 }
             }
@@ -1455,7 +1471,7 @@ ZB_HDN u32 parse_fast_warp(const C& w, const EncWork& W, const u8* src, size_t s
             ip0 -= (int)back; mpos -= (int)back;
             mLength = 4 + back;
             mLength += wcount(w, src, (u32)n, (u32)ip0 + mLength, (u32)mpos + mLength);
-            if (lane == 0) { W.seqLL[nbSeq] = (u32)(ip0 - anchor); W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = mLength; }
+            if (lane == 0) { W.put(nbSeq, (u32)(ip0 - anchor), 1, mLength); }
         } else {
             int const le = 2 * e + (kindE == 2 ? 1 : 0);
             ip0 = aE + (kindE == 2 ? 1 : 0); cur = ip0;
@@ -1465,7 +1481,7 @@ ZB_HDN u32 parse_fast_warp(const C& w, const EncWork& W, const u8* src, size_t s
             u32 const back = maxBack ? wcatchup(w, src, (u32)ip0, (u32)mpos, maxBack) : 0;
             u32 const fwd = wcount(w, src, (u32)n, (u32)ip0 + 4, (u32)mpos + 4);
             ip0 -= (int)back; mLength = 4 + back + fwd;
-            if (lane == 0) { W.seqLL[nbSeq] = (u32)(ip0 - anchor); W.seqOF[nbSeq] = rep1 + 3; W.seqML[nbSeq] = mLength; }
+            if (lane == 0) { W.put(nbSeq, (u32)(ip0 - anchor), rep1 + 3, mLength); }
         }
         nbSeq++;
         ip0 += (int)mLength; anchor = ip0;
@@ -1484,7 +1500,7 @@ ZB_HDN u32 parse_fast_warp(const C& w, const EncWork& W, const u8* src, size_t s
                     if (lane == 0) {
                         u64 const d0 = load64(src + ip0);
                         T[hashSv(d0, hlog, mls)] = cell((u32)ip0 + 2, tag4((u32)d0));
-                        W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = rLength;
+                        W.put(nbSeq, 0, 1, rLength);
                     }
                     nbSeq++; ip0 += (int)rLength; anchor = ip0;
                     w.sync();
@@ -1814,13 +1830,13 @@ ZB_HDN u32 parse_lazy(const EncWork& W, const u8* src, size_t srcSize, u32 hashL
                 offset_2 = offset_1; offset_1 = (u32)off;
             }
         }
-        W.seqLL[nbSeq] = (u32)(start - anchor); W.seqOF[nbSeq] = (u32)offBase; W.seqML[nbSeq] = (u32)matchLength; nbSeq++;
+        W.put(nbSeq, (u32)(start - anchor), (u32)offBase, (u32)matchLength); nbSeq++;
         anchor = ip = start + matchLength;
         if (ms.lazySkipping) { if (useRow) row_fill_cache(ms, ms.nextToUpdate, ilimit); ms.lazySkipping = false; }
         while (((ip <= ilimit) && (offset_2 > 0)) && (load32(ip) == load32(ip - offset_2))) {
             matchLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
             u32 const tmp = offset_2; offset_2 = offset_1; offset_1 = tmp;
-            W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = (u32)matchLength; nbSeq++;
+            W.put(nbSeq, 0, 1, (u32)matchLength); nbSeq++;
             ip += matchLength; anchor = ip;
         }
     }
@@ -1983,14 +1999,14 @@ ZB_HDN u32 parse_lazy_warp(const C& w, const EncWork& W, const u8* src, size_t s
                 offset_2 = offset_1; offset_1 = (u32)off;
             }
         }
-        if (w.lane == 0) { W.seqLL[nbSeq] = (u32)(start - anchor); W.seqOF[nbSeq] = (u32)offBase; W.seqML[nbSeq] = (u32)matchLength; }
+        if (w.lane == 0) { W.put(nbSeq, (u32)(start - anchor), (u32)offBase, (u32)matchLength); }
         nbSeq++;
         anchor = ip = start + matchLength;
         if (ms.lazySkipping) { if (useRow) row_fill_cache(ms, ms.nextToUpdate, ilimit); ms.lazySkipping = false; }
         while (((ip <= ilimit) && (offset_2 > 0)) && (load32(ip) == load32(ip - offset_2))) {
             matchLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
             u32 const tmp = offset_2; offset_2 = offset_1; offset_1 = tmp;
-            if (w.lane == 0) { W.seqLL[nbSeq] = 0; W.seqOF[nbSeq] = 1; W.seqML[nbSeq] = (u32)matchLength; }
+            if (w.lane == 0) { W.put(nbSeq, 0, 1, (u32)matchLength); }
             nbSeq++;
             ip += matchLength; anchor = ip;
         }
@@ -2008,11 +2024,15 @@ ZB_HDN u32 parse_lazy_warp(const C& w, const EncWork& W, const u8* src, size_t s
 constexpr u32 FRAME_CHECKSUM = 1, FRAME_NO_CONTENT_SIZE = 2;      // frameFlags: ZSTD_c_checksumFlag = 1, ZSTD_c_contentSizeFlag = 0
 constexpr u32 PARSE_SKIPPED = 0xFFFFFFFFu;     // nbSeq marker: srcSize < 7, the block is stored raw (ZSTD_buildSeqStore :3273-3280)
 
-template <class C>
+// ONLY = 0: every parser is compiled in.  ONLY = S_dfast / S_fast: the caller guarantees that this level selects that
+// strategy for every input size, so the kernel holds a single cooperative parser (64 registers without spills; the
+// all-in-one instantiation needs ~1 KB of stack).
+template <class C, u32 ONLY = 0>
 ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t srcSize, int level, u32* nbSeqOut, u32* lastLLOut) {
     CParams cp;
     *nbSeqOut = PARSE_SKIPPED; *lastLLOut = 0;
     if (!get_cparams(&cp, level, srcSize)) return ERR(E_parameter_unsupported);
+    if (ONLY != 0 && cp.strategy != ONLY) return ERR(E_GENERIC);
     if (srcSize < 7) return 0;
     {   // fresh tables: zero the used part (16-byte stores; the workspace is 16-byte aligned)
         u32 const nL = (1u << cp.hashLog) / 4;
@@ -2026,13 +2046,13 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
         for (u32 i = (u32)w.lane; i < nS; i += C::W) qS[i] = z;
         w.sync(); }
     u32 nbSeq = 0, lastLL = 0;
-    if (C::W > 1 && cp.strategy == S_dfast) {
+    if (C::W > 1 && (ONLY == S_dfast || (ONLY == 0 && cp.strategy == S_dfast))) {
         nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
-    } else if (C::W > 1 && cp.strategy == S_fast) {
+    } else if (C::W > 1 && (ONLY == S_fast || (ONLY == 0 && cp.strategy == S_fast))) {
         nbSeq = parse_fast_warp(w, W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
-    } else if (C::W > 1 && cp.strategy >= S_greedy && cp.strategy <= S_lazy2 && cp.windowLog > 14) {
+    } else if (ONLY == 0 && C::W > 1 && cp.strategy >= S_greedy && cp.strategy <= S_lazy2 && cp.windowLog > 14) {
         nbSeq = parse_lazy_warp(w, W, src, srcSize, cp.hashLog, cp.searchLog, cp.minMatch, cp.strategy - S_greedy, &lastLL);
-    } else {
+    } else if (ONLY == 0) {
         if (w.lane == 0) {
             if (cp.strategy >= S_greedy) nbSeq = parse_lazy(W, src, srcSize, cp.hashLog, cp.chainLog, cp.searchLog, cp.minMatch, cp.strategy == S_btlazy2 ? 2 : cp.strategy - S_greedy,
                                                           cp.strategy == S_btlazy2 ? 2u : cp.windowLog > 14 ? 1u : 0u, &lastLL);
@@ -2090,7 +2110,9 @@ ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, 
             size_t sp = 0;
             for (u32 base = 0; base < nbSeq; base += C::W) {
                 u32 const i = base + (u32)w.lane;
-                u32 const ll = i < nbSeq ? W.seqLL[i] : 0, ml = i < nbSeq ? W.seqML[i] : 0;
+                Seq q; q.ll = 0; q.of = 0; q.ml = 0; q.pad = 0;
+                if (i < nbSeq) q = W.get(i);
+                u32 const ll = q.ll, ml = q.ml;
                 u32 const lpre = w.exscan(ll), spre = w.exscan(ll + ml);
                 if (ll && ll <= 32) copy_fwd(W.lit + litSize + lpre, src + sp + spre, ll);
                 u32 big = w.ballot(ll > 32);
