@@ -1,0 +1,32 @@
+"""Small end-to-end pass for compute-sanitizer (memcheck): every kernel on a few frames of every kind.
+usage: compute-sanitizer --tool memcheck python scripts/gpu_sanitize.py"""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
+from zstd_jni_b200 import corpus
+from zstd_jni_b200.zstd import ZstdBatchContext, Zstd, ZstdCompressCtx
+
+rng = np.random.default_rng(1)
+chunks = [corpus.chunk(i).tobytes() for i in range(8)] + [corpus.chunk(i)[: int(rng.integers(1, 131072))].tobytes() for i in range(8)] + [b"", b"a", bytes(7), bytes(131072)]
+with ZstdBatchContext(0) as b:
+    for level in (3, 1, -2, 5, 9, 12):
+        todo = [c for c in chunks if level < 11 or len(c) > 16384]
+        frames = b.compressBatch(todo, level)
+        back = b.decompressBatch(frames, [len(c) for c in todo])
+        assert back == todo, level
+        print("level", level, "ok", sum(map(len, frames)), flush=True)
+    # corrupted frames: error paths of the staged and the fused decoder
+    frames = b.compressBatch(chunks[:8], 3)
+    bad = []
+    for f in frames:
+        a = bytearray(f); a[int(rng.integers(9, len(a)))] ^= 0x5A; bad.append(bytes(a))
+    res = b.decompressBatch(bad, [131072] * len(bad), raise_on_error=False)
+    print("corrupted:", [r if isinstance(r, int) else len(r) for r in res], flush=True)
+# libzstd-compatible one-shot layer, flags, multi-frame extension, streaming-style multi-block decode
+with ZstdCompressCtx() as c:
+    c.setLevel(3).setChecksum(True)
+    z = c.compress(chunks[0]); assert Zstd.decompress(z, len(chunks[0])) == chunks[0]
+    c.setMultiFrame(True)
+    big = b"".join(chunks[:3]); z = c.compress(big); assert Zstd.decompress(z, len(big)) == big
+print("sanitize script done")
