@@ -165,6 +165,27 @@ ZSTDB200_API size_t zstdb200_compress_batch(zstdb200_ctx* ctx, int level, size_t
 ZSTDB200_API size_t zstdb200_decompress_batch(zstdb200_ctx* ctx, size_t n, const void* const* src, const size_t* srcSize,
                                               void* const* dst, const size_t* dstCapacity, size_t* dstSize);
 
+/* ---- sequences: the GPU match finder behind the reference's sequence-level plug points
+ * ZSTD_Sequence is N/zstd.h:1315-1350.  zstdb200_generate_sequences is ZSTD_generateSequences
+ * (N/compress/zstd_compress.c:3520-3553) for n independent blocks of <= 128 KB: block i yields the records the reference
+ * writes for a one-shot input of that size at `level` -- its sequences with raw offsets and `rep`, then the block
+ * delimiter {0, last literals, 0, 0}.  nbSeqs[i] = number of records or an error code (capacity too small:
+ * dstSize_tooSmall; srcSize < 7: sequenceProducer_failed and an empty block: 0 records, as in the reference). */
+typedef struct { unsigned int offset; unsigned int litLength; unsigned int matchLength; unsigned int rep; } ZSTD_Sequence;
+ZSTDB200_API size_t zstdb200_generate_sequences(zstdb200_ctx* ctx, int level, size_t n, const void* const* src, const size_t* srcSize,
+                                                ZSTD_Sequence* const* outSeqs, const size_t* outSeqsCapacity, size_t* nbSeqs);
+/* A block-level external sequence producer of type ZSTD_sequenceProducer_F (N/zstd.h:2820-2900), to be registered with
+ * ZSTD_registerSequenceProducer -- from Java: Zstd.registerSequenceProducer / ZstdCompressCtx.registerSequenceProducer
+ * with a J/SequenceProducer.java whose getFunctionPointer() returns &zstdb200_sequenceProducer and whose createState() /
+ * freeState() call the two functions below (N/jni_zstd.c registerSequenceProducer, N/jni_fast_zstd.c).  libzstd keeps
+ * the frame, the block loop and the entropy stage; the match finding of every block runs on the GPU.  Blocks are parsed
+ * independently (no matches into earlier blocks).  Returns the number of records or ZSTD_SEQUENCE_PRODUCER_ERROR
+ * ((size_t)-1): no device, dictSize != 0, level without a GPU parser (>= 13). */
+ZSTDB200_API void* zstdb200_createSequenceProducerState(int device);
+ZSTDB200_API void zstdb200_freeSequenceProducerState(void* state);
+ZSTDB200_API size_t zstdb200_sequenceProducer(void* state, ZSTD_Sequence* outSeqs, size_t outSeqsCapacity, const void* src, size_t srcSize,
+                                              const void* dict, size_t dictSize, int compressionLevel, size_t windowSize);
+
 /* Device-memory calls (asynchronous on `stream`, a cudaStream_t passed as void*; 0 = the context's stream).
  * All pointers are device pointers; offsets are uint64 arrays of n+1 entries (item i = [off[i], off[i+1])).
  * compress_device writes frame i at d_slots + i*slotStride (slotStride >= ZSTD_compressBound(max chunk) + 32)

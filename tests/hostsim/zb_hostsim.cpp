@@ -133,6 +133,35 @@ size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     return r;
 }
 
+// ---- sequence export (ZSTD_Sequence records of one block): parse + export_sequences on 1 lane (emu = 0) or on the emulator
+size_t zbh_generate_sequences(void* outSeqs, size_t outCapacity, const void* src, size_t srcSize, int level, int emu) {
+    using namespace zb;
+    if (srcSize > BLOCKSIZE_MAX) return ERR(E_srcSize_wrong);
+    u8* wk = (u8*)calloc(1, enc_work_bytes() + 64);
+    EncWork W = enc_work_carve(wk);
+    u8* in = (u8*)calloc(1, srcSize + 64);
+    memcpy(in + 16, src, srcSize);
+    ZSeq* out = (ZSeq*)aligned_alloc(16, sizeof(ZSeq) * (MAX_SEQ + 2));
+    size_t r; u32 n = 0;
+    if (emu) {
+        size_t results[32]; u32 nbSeqs[32], lastLLs[32], counts[32];
+        run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = parse_stage(w, W, in + 16, srcSize, level, &nbSeqs[w.lane], &lastLLs[w.lane]); });
+        r = results[0];
+        if (!isErr(r)) {
+            run_warp<32>([&](const WarpEmuT<32>& w) { counts[w.lane] = export_sequences(w, W.seq, nbSeqs[0], lastLLs[0], srcSize, out); });
+            n = counts[0];
+            for (int i = 1; i < 32; i++) if (counts[i] != n) r = ERR(E_GENERIC);
+        }
+    } else {
+        WarpHost w; u32 nbSeq = 0, lastLL = 0;
+        r = parse_stage(w, W, in + 16, srcSize, level, &nbSeq, &lastLL);
+        if (!isErr(r)) n = export_sequences(w, W.seq, nbSeq, lastLL, srcSize, out);
+    }
+    if (!isErr(r)) { if (n > outCapacity) r = ERR(E_dstSize_tooSmall); else { memcpy(outSeqs, out, sizeof(ZSeq) * n); r = n; } }
+    free(wk); free(in); free(out);
+    return r;
+}
+
 size_t zbh_sizeof_dec_shared() { return sizeof(zb::DecShared); }
 size_t zbh_sizeof_enc_shared() { return sizeof(zb::EncShared); }
 }

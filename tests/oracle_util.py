@@ -65,6 +65,9 @@ def ref():
         ("ZSTD_decompressDCtx", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
         ("ZSTD_compressStream2", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
         ("ZSTD_versionString", C.c_char_p, []),
+        ("ZSTD_generateSequences", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+        ("ZSTD_sequenceBound", C.c_size_t, [C.c_size_t]),
+        ("ZSTD_registerSequenceProducer", None, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ])
 
 
@@ -77,6 +80,7 @@ def hostsim():
         ("zbe_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
         ("zbe_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         ("zbp_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("zbh_generate_sequences", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int]),
     ])
     if L is None:
         raise RuntimeError(f"{HOSTSIM_PATH} missing: run __graft_entry__.build()")
@@ -200,3 +204,27 @@ def ref_stream_compress(data: bytes, level: int, slice_size: int = 131072, check
             break
     R.ZSTD_freeCCtx(cctx)
     return bytes(out)
+
+
+# ---- sequences (ZSTD_Sequence records: offset, litLength, matchLength, rep -- 4 x u32)
+def ref_generate_sequences(data: bytes, level: int):
+    """ZSTD_generateSequences of the compiled reference: (n, 4) uint32 array, or a negative error code."""
+    import numpy as np
+    R = ref()
+    cctx = R.ZSTD_createCCtx()
+    try:
+        R.ZSTD_CCtx_setParameter(cctx, 100, level)
+        cap = R.ZSTD_sequenceBound(len(data)) + 2
+        out = np.zeros((cap, 4), dtype=np.uint32)
+        n = R.ZSTD_generateSequences(cctx, out.ctypes.data, cap, data, len(data))
+        return out[:n].copy() if n <= ERR_MAX else -((1 << 64) - n)
+    finally:
+        R.ZSTD_freeCCtx(cctx)
+
+
+def hostsim_generate_sequences(data: bytes, level: int, emu: bool = False):
+    import numpy as np
+    cap = len(data) // 3 + 16
+    out = np.zeros((cap, 4), dtype=np.uint32)
+    n = hostsim().zbh_generate_sequences(out.ctypes.data, cap, data, len(data), level, 1 if emu else 0)
+    return out[:n].copy() if n <= ERR_MAX else -((1 << 64) - n)

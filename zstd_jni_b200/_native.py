@@ -94,6 +94,10 @@ def lib() -> C.CDLL:
     sig("zstdb200_decompress_frames", sz, vp, vp, c_size_p, sz, vp, sz, c_size_p)
     sig("zstdb200_compress_batch", sz, vp, i, sz, C.POINTER(vp), c_size_p, C.POINTER(vp), c_size_p, c_size_p)
     sig("zstdb200_decompress_batch", sz, vp, sz, C.POINTER(vp), c_size_p, C.POINTER(vp), c_size_p, c_size_p)
+    sig("zstdb200_generate_sequences", sz, vp, i, sz, C.POINTER(vp), c_size_p, C.POINTER(vp), c_size_p, c_size_p)
+    sig("zstdb200_createSequenceProducerState", vp, i)
+    sig("zstdb200_freeSequenceProducerState", None, vp)
+    sig("zstdb200_sequenceProducer", sz, vp, vp, sz, vp, sz, vp, sz, i, sz)
     sig("zstdb200_compress_device", sz, vp, i, sz, vp, vp, vp, sz, vp, vp)
     sig("zstdb200_compact_device", sz, vp, sz, vp, sz, vp, vp, vp, vp)
     sig("zstdb200_decompress_device", sz, vp, sz, vp, vp, vp, vp, vp, vp)

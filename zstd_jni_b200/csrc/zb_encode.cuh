@@ -32,6 +32,7 @@ struct CParams { u32 windowLog, chainLog, hashLog, searchLog, minMatch, targetLe
 enum : u32 { S_fast = 1, S_dfast = 2, S_greedy = 3, S_lazy = 4, S_lazy2 = 5, S_btlazy2 = 6 };
 
 constexpr u32 MAX_SEQ = (BLOCKSIZE_MAX / 4) + 8;
+constexpr u32 PARSE_SKIPPED = 0xFFFFFFFFu;     // nbSeq marker: srcSize < 7, the block is stored raw (ZSTD_buildSeqStore :3273-3280)
 constexpr u32 ENC_HASHLOG_MAX = 18;     // largest hashLog / chainLog of the supported rows
 
 // ZSTD_getCParams_internal (:7759-7782) + ZSTD_adjustCParams_internal (:1472-1609) for a known
@@ -2016,13 +2017,52 @@ ZB_HDN u32 parse_lazy_warp(const C& w, const EncWork& W, const u8* src, size_t s
     return nbSeq;
 }
 
+// ------------------------------------------------------------------ sequence export
+// The parse of one block in the layout of the reference's public ZSTD_Sequence (N/zstd.h:1315-1350), as
+// ZSTD_generateSequences / ZSTD_copyBlockSequences (N/compress/zstd_compress.c:3429-3512) write it for the first block of
+// a frame (repcode history {1,4,8}): one record per sequence with the raw offset and the `rep` field resolved, then one
+// {offset 0, litLength = trailing literals, matchLength 0} record -- the block delimiter.  This is also what an external
+// sequence producer (ZSTD_sequenceProducer_F, N/zstd.h:2820-2900) hands back to libzstd.
+// Rows of W sequences: loads and stores are one 16-byte record per lane; the repcode history is a serial scan that
+// every lane follows with shuffles (three registers), lane k keeping the offset of its own sequence.
+// A block the reference would not parse (srcSize < 7, PARSE_SKIPPED) is exported as literals only.  Returns the number
+// of records (uniform), at most MAX_SEQ + 1.
+struct alignas(16) ZSeq { u32 offset, litLength, matchLength, rep; };
+template <class C>
+ZB_HDN u32 export_sequences(const C& w, const Seq* in, u32 nbSeq, u32 lastLL, size_t srcSize, ZSeq* out) {
+    if (nbSeq == PARSE_SKIPPED) { nbSeq = 0; lastLL = (u32)srcSize; }
+    u32 rep0 = 1, rep1 = 4, rep2 = 8;
+    for (u32 base = 0; base < nbSeq; base += C::W) {
+        u32 const i = base + (u32)w.lane;
+        Seq q; q.ll = 0; q.of = 0; q.ml = 0; q.pad = 0;
+        if (i < nbSeq) q = in[i];
+        u32 const rows = (nbSeq - base < (u32)C::W) ? nbSeq - base : (u32)C::W;
+        u32 raw = 0, repField = 0;
+        for (u32 k = 0; k < rows; k++) {
+            u32 const of = w.shfl(q.of, (int)k), ll0 = w.shfl(q.ll, (int)k) == 0 ? 1u : 0u;
+            u32 r, f = 0;
+            if (of > 3) { r = of - 3; rep2 = rep1; rep1 = rep0; rep0 = r; }
+            else {                                             // repcode 1..3 (ZSTD_updateRep, zstd_compress_internal.h:817-835)
+                f = of;
+                u32 const rc = of - 1 + ll0;
+                r = rc == 0 ? rep0 : rc == 1 ? rep1 : rc == 2 ? rep2 : rep0 - 1;
+                if (rc > 0) { if (rc >= 2) rep2 = rep1; rep1 = rep0; rep0 = r; }
+            }
+            if ((u32)w.lane == k) { raw = r; repField = f; }
+        }
+        if (i < nbSeq) { ZSeq z; z.offset = raw; z.litLength = q.ll; z.matchLength = q.ml; z.rep = repField; out[i] = z; }
+    }
+    if (w.lane == 0) { ZSeq z; z.offset = 0; z.litLength = lastLL; z.matchLength = 0; z.rep = 0; out[nbSeq] = z; }
+    w.sync();
+    return nbSeq + 1;
+}
+
 // ------------------------------------------------------------------ frame
 // A chunk becomes a frame in two stages that may run in different kernels (and with different group widths):
 //   parse_stage   match finding -> sequences (W.seq*), their count and the trailing literal run
 //   encode_stage  frame/block headers, literal gathering, Huffman + FSE entropy stage
 // Together they emit what ZSTD_compress2 would with dstCapacity = ZSTD_compressBound(srcSize).
 constexpr u32 FRAME_CHECKSUM = 1, FRAME_NO_CONTENT_SIZE = 2;      // frameFlags: ZSTD_c_checksumFlag = 1, ZSTD_c_contentSizeFlag = 0
-constexpr u32 PARSE_SKIPPED = 0xFFFFFFFFu;     // nbSeq marker: srcSize < 7, the block is stored raw (ZSTD_buildSeqStore :3273-3280)
 
 // ONLY = 0: every parser is compiled in.  ONLY = S_dfast / S_fast: the caller guarantees that this level selects that
 // strategy for every input size, so the kernel holds a single cooperative parser (64 registers without spills; the

@@ -369,6 +369,46 @@ class ZstdBatchContext(_AutoClose):
         return [outs[i][: dsz[i]].tobytes() if not N.is_error(dsz[i]) else -N.error_code(dsz[i]) for i in range(k)]
 
 
+    def generateSequences(self, blocks: Sequence, level: int = 3, raise_on_error: bool = True):
+        """ZSTD_generateSequences for every block (<= 128 KB each): list of (n, 4) uint32 arrays with the columns of
+        ZSTD_Sequence (offset, litLength, matchLength, rep); the last row of a block is its delimiter."""
+        L = N.lib()
+        k = len(blocks)
+        bufs = [_buf(b) for b in blocks]
+        src = (C.c_void_p * k)(*[b[0] for b in bufs])
+        ssz = (C.c_size_t * k)(*[b[1] for b in bufs])
+        outs = [np.zeros((b[1] // 3 + 2, 4), dtype=np.uint32) for b in bufs]         # ZSTD_sequenceBound
+        dst = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
+        cap = (C.c_size_t * k)(*[o.shape[0] for o in outs])
+        nb = (C.c_size_t * k)()
+        r = L.zstdb200_generate_sequences(self._live(), level, k, src, ssz, dst, cap, nb)
+        if N.is_error(r) and raise_on_error:
+            self._raise(r)
+        return [outs[i][: nb[i]] if not N.is_error(nb[i]) else -N.error_code(nb[i]) for i in range(k)]
+
+
+class B200SequenceProducer:
+    """A J/SequenceProducer.java implementation backed by the GPU match finder: the three methods return what
+    Zstd.registerSequenceProducer / ZstdCompressCtx.registerSequenceProducer pass on to ZSTD_registerSequenceProducer
+    (N/jni_zstd.c, N/jni_fast_zstd.c)."""
+
+    def __init__(self, device: int = -1):
+        self.device = device
+
+    def getFunctionPointer(self) -> int:
+        return C.cast(N.lib().zstdb200_sequenceProducer, C.c_void_p).value
+
+    def createState(self) -> int:
+        L = N.lib()
+        p = L.zstdb200_createSequenceProducerState(self.device)
+        if not p:
+            raise RuntimeError("zstdb200_createSequenceProducerState failed (no CPU fallback): " + L.zstdb200_last_error().decode())
+        return p
+
+    def freeState(self, statePointer: int) -> None:
+        N.lib().zstdb200_freeSequenceProducerState(statePointer)
+
+
 class ZstdOutputStream:
     """J/ZstdOutputStreamNoFinalizer.java:83-90,400-518 over ZSTD_compressStream2.
 
