@@ -299,9 +299,10 @@ def main():
     h_stream = torch.empty(n * stride, dtype=torch.uint8).pin_memory()
     h_back = torch.empty(n * CHUNK, dtype=torch.uint8).pin_memory()
     fsz = (C.c_size_t * n)(); tot = C.c_size_t(0); dsz = (C.c_size_t * n)()
+    dsz_in = (C.c_size_t * n)(*([CHUNK] * n))          # expected sizes (in) -> regenerated sizes (out): refreshed per step
     def e2e_step():
         check(L.zstdb200_compress_chunks(ctx.handle, args.level, h_src.data_ptr(), U, CHUNK, h_stream.data_ptr(), h_stream.numel(), fsz, C.byref(tot)))
-        for i in range(n): dsz[i] = CHUNK
+        C.memmove(dsz, dsz_in, C.sizeof(dsz))
         check(L.zstdb200_decompress_frames(ctx.handle, h_stream.data_ptr(), fsz, n, h_back.data_ptr(), h_back.numel(), dsz))
     e2e_step(); barrier()
     e2e_steps = max(1, min(args.steps, 3))

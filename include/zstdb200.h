@@ -47,12 +47,16 @@ typedef enum {
     ZSTD_c_checksumFlag = 201,
     ZSTD_c_dictIDFlag = 202,
     ZSTD_c_nbWorkers = 400,
+    ZSTD_c_format = 10,                 /* ZSTD_c_experimentalParam2 (N/zstd.h:2051): ZSTD_f_zstd1 / ZSTD_f_zstd1_magicless, N/jni_zstd.c:362-363 */
     /* extension of this library (not in libzstd): when non-zero, ZSTD_compress2 / ZSTD_compressCCtx accept inputs larger
      * than one block and write them as one independent frame per 128 KB -- a legal zstd stream (every decoder reads
      * concatenated frames) but NOT the bytes the reference would produce.  Off by default: without it such inputs are
      * refused with ZSTD_error_parameter_unsupported.  Environment default: ZSTDB200_MULTIFRAME=1. */
     ZSTDB200_c_multiFrame = 0xB200
 } ZSTD_cParameter;
+/* N/zstd.h:642-672 (ZSTD_dParameter): the two the JNI glue sets on this path, N/jni_zstd.c:403,413-414 */
+typedef enum { ZSTD_d_windowLogMax = 100, ZSTD_d_format = 1000 /* ZSTD_d_experimentalParam1 */ } ZSTD_dParameter;
+typedef enum { ZSTD_f_zstd1 = 0, ZSTD_f_zstd1_magicless = 1 } ZSTD_format_e;        /* N/zstd.h:1382-1389 */
 typedef enum { ZSTD_reset_session_only = 1, ZSTD_reset_parameters = 2, ZSTD_reset_session_and_parameters = 3 } ZSTD_ResetDirective;
 typedef enum { ZSTD_e_continue = 0, ZSTD_e_flush = 1, ZSTD_e_end = 2 } ZSTD_EndDirective;
 typedef struct { const void* src; size_t size; size_t pos; } ZSTD_inBuffer;    /* N/zstd.h:731-735 */
@@ -84,6 +88,10 @@ ZSTDB200_API size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, ZSTD_cParameter para
 ZSTDB200_API size_t ZSTD_CCtx_reset(ZSTD_CCtx* cctx, ZSTD_ResetDirective reset);   /* N/jni_fast_zstd.c:605,633 */
 ZSTDB200_API size_t ZSTD_DCtx_reset(ZSTD_DCtx* dctx, ZSTD_ResetDirective reset);   /* N/jni_fast_zstd.c:797,824 */
 ZSTDB200_API size_t ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* cctx, unsigned long long pledgedSrcSize);
+ZSTDB200_API size_t ZSTD_DCtx_setParameter(ZSTD_DCtx* dctx, ZSTD_dParameter param, int value);   /* N/jni_zstd.c:403,413-414 */
+/* N/jni_fast_zstd.c:373 (J/ZstdCompressCtx.getFrameProgression); the MT fields stay 0 */
+typedef struct { unsigned long long ingested, consumed, produced, flushed; unsigned currentJobID, nbActiveWorkers; } ZSTD_frameProgression;
+ZSTDB200_API ZSTD_frameProgression ZSTD_getFrameProgression(const ZSTD_CCtx* cctx);
 
 /* one-shot hot path:
  *   ZSTD_compress2       <- N/jni_fast_zstd.c:607,635 (compressDirectByteBuffer0 / compressByteArray0), N/jni_zstd.c:23
@@ -105,6 +113,26 @@ ZSTDB200_API size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* s
 
 /* frame inspection (host-side header walks): N/jni_zstd.c:70-117 (decompressedSize / findFrameCompressedSize) */
 ZSTDB200_API unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);
+/* frame header inspection, host side (N/zstd.h:1510-1545; N/jni_zstd.c:35 magicless sizes, :139,156 dictID of a frame) */
+typedef enum { ZSTD_frame, ZSTD_skippableFrame } ZSTD_FrameType_e;
+typedef struct {
+    unsigned long long frameContentSize;   /* ZSTD_CONTENTSIZE_UNKNOWN when absent; size of the skippable content for a skippable frame */
+    unsigned long long windowSize;
+    unsigned blockSizeMax;
+    ZSTD_FrameType_e frameType;
+    unsigned headerSize;
+    unsigned dictID;                       /* skippable frame: magic variant 0..15 */
+    unsigned checksumFlag;
+    unsigned _reserved1;
+    unsigned _reserved2;
+} ZSTD_FrameHeader;
+#define ZSTD_frameHeader ZSTD_FrameHeader  /* old name, used by N/jni_zstd.c:34 */
+ZSTDB200_API size_t ZSTD_getFrameHeader(ZSTD_FrameHeader* zfhPtr, const void* src, size_t srcSize);
+ZSTDB200_API size_t ZSTD_getFrameHeader_advanced(ZSTD_FrameHeader* zfhPtr, const void* src, size_t srcSize, ZSTD_format_e format);
+ZSTDB200_API size_t ZSTD_frameHeaderSize(const void* src, size_t srcSize);
+ZSTDB200_API unsigned ZSTD_isFrame(const void* buffer, size_t size);
+ZSTDB200_API unsigned ZSTD_isSkippableFrame(const void* buffer, size_t size);
+ZSTDB200_API unsigned ZSTD_getDictID_fromFrame(const void* src, size_t srcSize);     /* always the frame's field; dictionaries themselves are out of scope */
 ZSTDB200_API size_t ZSTD_findFrameCompressedSize(const void* src, size_t srcSize);
 ZSTDB200_API unsigned long long ZSTD_decompressBound(const void* src, size_t srcSize);
 

@@ -39,7 +39,9 @@ size_t zbh_compress_flags(void* dst, size_t dstCapacity, const void* src, size_t
     return r;
 }
 
-size_t zbh_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize) {
+size_t zbh_decompress_format(void* dst, size_t dstCapacity, const void* src, size_t srcSize, unsigned magicless);
+size_t zbh_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize) { return zbh_decompress_format(dst, dstCapacity, src, srcSize, 0); }
+size_t zbh_decompress_format(void* dst, size_t dstCapacity, const void* src, size_t srcSize, unsigned magicless) {
     using namespace zb;
     WarpHost w;
     DecShared* S = (DecShared*)calloc(1, sizeof(DecShared));
@@ -47,7 +49,7 @@ size_t zbh_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     u8* in = (u8*)calloc(1, srcSize + 64);
     memcpy(in + 16, src, srcSize);
     u8* out = (u8*)calloc(1, dstCapacity + 64);
-    size_t const r = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch);
+    size_t const r = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch, magicless);
     if (!isErr(r)) memcpy(dst, out + 16, r);
     free(S); free(scratch); free(in); free(out);
     return r;

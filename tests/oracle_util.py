@@ -65,6 +65,7 @@ def ref():
         ("ZSTD_decompressDCtx", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
         ("ZSTD_compressStream2", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
         ("ZSTD_versionString", C.c_char_p, []),
+        ("ZSTD_DCtx_setParameter", C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
         ("ZSTD_generateSequences", C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         ("ZSTD_sequenceBound", C.c_size_t, [C.c_size_t]),
         ("ZSTD_registerSequenceProducer", None, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -76,6 +77,7 @@ def hostsim():
         ("zbh_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
         ("zbh_compress_flags", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint]),
         ("zbh_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+        ("zbh_decompress_format", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_uint]),
         ("zbh_compress_bound", C.c_size_t, [C.c_size_t]),
         ("zbe_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
         ("zbe_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
@@ -116,16 +118,37 @@ def oracle_compress_flags(data: bytes, level: int, checksum: bool = False, conte
     return _call_flags(zso().zso_compress_flags, data, level, (1 if checksum else 0) | (0 if content_size else 2))
 
 
-def hostsim_compress_flags(data: bytes, level: int, checksum: bool = False, content_size: bool = True):
-    return _call_flags(hostsim().zbh_compress_flags, data, level, (1 if checksum else 0) | (0 if content_size else 2))
+def hostsim_compress_flags(data: bytes, level: int, checksum: bool = False, content_size: bool = True, magicless: bool = False):
+    return _call_flags(hostsim().zbh_compress_flags, data, level, (1 if checksum else 0) | (0 if content_size else 2) | (4 if magicless else 0))
 
 
-def ref_compress_flags(data: bytes, level: int, checksum: bool = False, content_size: bool = True):
+def hostsim_decompress_magicless(frame: bytes, cap: int):
+    out = C.create_string_buffer(max(cap, 1))
+    n = hostsim().zbh_decompress_format(out, cap, frame, len(frame), 1)
+    return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
+
+
+def ref_decompress_magicless(frame: bytes, cap: int):
+    """ZSTD_d_format = ZSTD_f_zstd1_magicless (J/ZstdDecompressCtx.setMagicless, N/jni_zstd.c:413-414)."""
+    R = ref()
+    dctx = R.ZSTD_createDCtx()
+    try:
+        assert R.ZSTD_DCtx_setParameter(dctx, 1000, 1) <= ERR_MAX
+        out = C.create_string_buffer(max(cap, 1))
+        n = R.ZSTD_decompressDCtx(dctx, out, cap, frame, len(frame))
+        return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
+    finally:
+        R.ZSTD_freeDCtx(dctx)
+
+
+def ref_compress_flags(data: bytes, level: int, checksum: bool = False, content_size: bool = True, magicless: bool = False):
     """The compiled reference through ZSTD_CCtx_setParameter + ZSTD_compress2 (what J/ZstdCompressCtx drives)."""
     R = ref()
     cctx = R.ZSTD_createCCtx()
     try:
         R.ZSTD_CCtx_setParameter(cctx, 100, level)
+        if magicless:
+            assert R.ZSTD_CCtx_setParameter(cctx, 10, 1) <= ERR_MAX      # ZSTD_c_format = ZSTD_f_zstd1_magicless
         R.ZSTD_CCtx_setParameter(cctx, 201, 1 if checksum else 0)
         R.ZSTD_CCtx_setParameter(cctx, 200, 1 if content_size else 0)
         cap = len(data) + (len(data) >> 8) + 1024

@@ -17,6 +17,16 @@ c_size_p = C.POINTER(C.c_size_t)
 c_u64_p = C.POINTER(C.c_uint64)
 
 
+class FrameHeader(C.Structure):          # ZSTD_FrameHeader, N/zstd.h:1512-1522
+    _fields_ = [("frameContentSize", C.c_ulonglong), ("windowSize", C.c_ulonglong), ("blockSizeMax", C.c_uint), ("frameType", C.c_int),
+                ("headerSize", C.c_uint), ("dictID", C.c_uint), ("checksumFlag", C.c_uint), ("_reserved1", C.c_uint), ("_reserved2", C.c_uint)]
+
+
+class FrameProgression(C.Structure):     # ZSTD_frameProgression, N/zstd.h:2736-2743
+    _fields_ = [("ingested", C.c_ulonglong), ("consumed", C.c_ulonglong), ("produced", C.c_ulonglong), ("flushed", C.c_ulonglong),
+                ("currentJobID", C.c_uint), ("nbActiveWorkers", C.c_uint)]
+
+
 class NativeLibraryMissing(RuntimeError):
     pass
 
@@ -64,6 +74,14 @@ def lib() -> C.CDLL:
     sig("ZSTD_compressCCtx", sz, vp, vp, sz, vp, sz, i)
     sig("ZSTD_decompressDCtx", sz, vp, vp, sz, vp, sz)
     sig("ZSTD_decompress", sz, vp, sz, vp, sz)
+    sig("ZSTD_DCtx_setParameter", sz, vp, i, i)
+    sig("ZSTD_getFrameProgression", FrameProgression, vp)
+    sig("ZSTD_getFrameHeader", sz, C.POINTER(FrameHeader), vp, sz)
+    sig("ZSTD_getFrameHeader_advanced", sz, C.POINTER(FrameHeader), vp, sz, i)
+    sig("ZSTD_frameHeaderSize", sz, vp, sz)
+    sig("ZSTD_isFrame", C.c_uint, vp, sz)
+    sig("ZSTD_isSkippableFrame", C.c_uint, vp, sz)
+    sig("ZSTD_getDictID_fromFrame", C.c_uint, vp, sz)
     sig("ZSTD_getFrameContentSize", C.c_ulonglong, vp, sz)
     sig("ZSTD_findFrameCompressedSize", sz, vp, sz)
     sig("ZSTD_decompressBound", C.c_ulonglong, vp, sz)

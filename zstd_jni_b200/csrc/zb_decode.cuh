@@ -550,14 +550,17 @@ ZB_HDN size_t decode_block(const C& w, DecShared& S, const u8* frameStart, u8* o
 }
 
 // ------------------------------------------------------------ frame layer
-struct FrameHeader { u32 headerSize; u64 contentSize; u64 windowSize; u32 blockSizeMax; u32 checksum, skippable, skipLen, hasContentSize; };
+struct FrameHeader { u32 headerSize; u64 contentSize; u64 windowSize; u32 blockSizeMax; u32 checksum, skippable, skipLen, hasContentSize, dictID; };
 
-// ZSTD_getFrameHeader_advanced :447-551.  0 = ok, >0 = bytes wanted, or error
-ZB_HDN size_t read_frame_header(FrameHeader* fh, const u8* src, size_t srcSize) {
+// ZSTD_getFrameHeader_advanced :447-551.  0 = ok, >0 = bytes wanted, or error.
+// magicless != 0: ZSTD_f_zstd1_magicless (N/zstd.h:1386) -- the frame starts at its descriptor byte, no magic number,
+// hence no skippable frames either.
+ZB_HDN size_t read_frame_header(FrameHeader* fh, const u8* src, size_t srcSize, u32 magicless = 0) {
     fh->headerSize = 0; fh->contentSize = 0; fh->windowSize = 0; fh->blockSizeMax = 0;
-    fh->checksum = fh->skippable = fh->skipLen = 0; fh->hasContentSize = 0;
-    if (srcSize < 5) {
-        if (srcSize > 0) {
+    fh->checksum = fh->skippable = fh->skipLen = 0; fh->hasContentSize = 0; fh->dictID = 0;
+    u32 const mlen = magicless ? 0u : 4u;                 // ZSTD_startingInputLength - 1
+    if (srcSize < mlen + 1) {
+        if (srcSize > 0 && !magicless) {
             u32 const k = (u32)(srcSize < 4 ? srcSize : 4);
             u32 got = 0; for (u32 i = 0; i < k; i++) got |= (u32)src[i] << (8 * i);
             u32 const m = (k == 4) ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1);
@@ -565,29 +568,32 @@ ZB_HDN size_t read_frame_header(FrameHeader* fh, const u8* src, size_t srcSize) 
                 if ((got & m & 0xFFFFFFF0u) != (0x184D2A50u & m & 0xFFFFFFF0u)) return ERR(E_prefix_unknown);
             }
         }
-        return 5;
+        return mlen + 1;
     }
-    u32 const magic = load32(src);
-    if (magic != MAGIC) {
-        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
-            if (srcSize < 8) return 8;
-            fh->skippable = 1; fh->skipLen = load32(src + 4); fh->headerSize = 8;
-            return 0;
+    if (!magicless) {
+        u32 const magic = load32(src);
+        if (magic != MAGIC) {
+            if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
+                if (srcSize < 8) return 8;
+                fh->skippable = 1; fh->skipLen = load32(src + 4); fh->headerSize = 8; fh->dictID = magic - 0x184D2A50u;
+                return 0;
+            }
+            return ERR(E_prefix_unknown);
         }
-        return ERR(E_prefix_unknown);
     }
-    u32 const fhd = src[4], dictID = fhd & 3, single = (fhd >> 5) & 1, fcsID = fhd >> 6;
+    u32 const fhd = src[mlen], dictID = fhd & 3, single = (fhd >> 5) & 1, fcsID = fhd >> 6;
     u32 const didSize = dictID == 3 ? 4 : dictID, fcsSize = fcsID == 0 ? 0 : (1u << fcsID);
-    size_t const hs = 5 + !single + didSize + fcsSize + (single && !fcsID);
+    size_t const hs = mlen + 1 + !single + didSize + fcsSize + (single && !fcsID);
     if (srcSize < hs) return hs;
     fh->headerSize = (u32)hs;
     if (fhd & 0x08) return ERR(E_frameParameter_unsupported);
-    size_t pos = 5;
+    size_t pos = mlen + 1;
     if (!single) {
         u32 const wl = src[pos++], windowLog = (wl >> 3) + 10;
         if (windowLog > 31) return ERR(E_frameParameter_windowTooLarge);
         fh->windowSize = 1ull << windowLog; fh->windowSize += (fh->windowSize >> 3) * (wl & 7);
     }
+    for (u32 i = 0; i < didSize; i++) fh->dictID |= (u32)src[pos + i] << (8 * i);
     pos += didSize;
     fh->hasContentSize = 1;
     switch (fcsID) {
@@ -605,18 +611,18 @@ ZB_HDN size_t read_frame_header(FrameHeader* fh, const u8* src, size_t srcSize) 
 // ZSTD_decompressMultiFrame :1070-1169 + ZSTD_decompressFrame :953-1066.
 // Uniform across the warp; returns regenerated size or an error code.
 template <class C>
-ZB_HDN size_t decompress_item(const C& w, DecShared& S, const u8* src, size_t srcSize, u8* dst, size_t dstCapacity, u8* scratch) {
+ZB_HDN size_t decompress_item(const C& w, DecShared& S, const u8* src, size_t srcSize, u8* dst, size_t dstCapacity, u8* scratch, u32 magicless = 0) {
     size_t total = 0; bool more = false;
-    while (srcSize >= 4) {
-        if (srcSize >= 8 && (load32(src) & 0xFFFFFFF0u) == 0x184D2A50u) {
+    while (srcSize >= (magicless ? 1u : 4u)) {
+        if (!magicless && srcSize >= 8 && (load32(src) & 0xFFFFFFF0u) == 0x184D2A50u) {
             size_t const skip = 8 + (size_t)load32(src + 4);
             if (skip > srcSize) return ERR(E_srcSize_wrong);
             src += skip; srcSize -= skip; continue;
         }
         // ---- one frame
-        if (srcSize < 6 + 3) return ERR(E_srcSize_wrong);
+        if (srcSize < (magicless ? 2u : 6u) + 3) return ERR(E_srcSize_wrong);     // ZSTD_FRAMEHEADERSIZE_MIN(format) + block header
         FrameHeader fh;
-        {   size_t const r = read_frame_header(&fh, src, srcSize);
+        {   size_t const r = read_frame_header(&fh, src, srcSize, magicless);
             if (isErr(r)) return (more && r == ERR(E_prefix_unknown)) ? ERR(E_srcSize_wrong) : r;
             if (r > 0) return ERR(E_srcSize_wrong);
             if (srcSize < fh.headerSize + 3) return ERR(E_srcSize_wrong);

@@ -55,7 +55,23 @@ static const LevelTables h_levels = ZB_LEVEL_TABLES_INIT;
 #define ZB_LEVELS (::zb::h_levels)
 #endif
 
-ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize) {
+// ZSTD_adjustCParams_internal :1472-1609 for a known srcSize <= 128 KB without dictionary (the row-hash cap :1596-1606
+// cannot bind: hashLog <= windowLog + 1 <= 18)
+ZB_HD void adjust_cparams(CParams& cp, size_t srcSize) {
+    u32 const tSize = (u32)srcSize;
+    u32 const srcLog = (tSize < 64) ? 6 : highbit32(tSize - 1) + 1;
+    if (cp.windowLog > srcLog) cp.windowLog = srcLog;
+    if (cp.hashLog > cp.windowLog + 1) cp.hashLog = cp.windowLog + 1;
+    {   u32 const cycleLog = cp.chainLog - (cp.strategy >= S_btlazy2 ? 1 : 0);      // ZSTD_cycleLog
+        if (cycleLog > cp.windowLog) cp.chainLog -= (cycleLog - cp.windowLog); }
+    if (cp.windowLog < 10) cp.windowLog = 10;
+}
+
+// `ov`: explicit parameters (ZSTD_c_windowLog ... ZSTD_c_strategy, 0 = not set) as ZSTD_getCParamsFromCCtxParams :1637-1651
+// applies them: over the adjusted row of the level (ZSTD_overrideCParams :1623-1635), then adjusted again.
+// checkWindow: refuse parameter sets whose window does not cover the input (matches would have to respect a sliding
+// window inside the block, which these parsers do not implement).
+ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize, const CParams* ov = nullptr, bool checkWindow = true) {
     // rows 0..12 of the "<=128 KB" table and 0..10 of the "<=16 KB" table (clevels.h:78-92,104-116).  greedy / lazy / lazy2
     // run with the row-based match finder when windowLog > 14 (ZSTD_resolveRowMatchFinderMode, zstd_compress.c:238-245),
     // i.e. for every srcSize > 16 KB, and with the hash-chain finder below; btlazy2 uses the binary tree.  The rows from
@@ -68,13 +84,19 @@ ZB_HDN bool get_cparams(CParams* out, int level, size_t srcSize) {
     if (row > (small ? 10 : 12)) return false;
     CParams cp = small ? ZB_LEVELS.t16[row] : ZB_LEVELS.t128[row];
     if (level < 0) { int const l = level < -(1 << 17) ? -(1 << 17) : level; cp.targetLength = (u32)(-l); }
-    u32 const tSize = (u32)srcSize;
-    u32 const srcLog = (tSize < 64) ? 6 : highbit32(tSize - 1) + 1;
-    if (cp.windowLog > srcLog) cp.windowLog = srcLog;
-    if (cp.hashLog > cp.windowLog + 1) cp.hashLog = cp.windowLog + 1;
-    {   u32 const cycleLog = cp.chainLog - (cp.strategy >= S_btlazy2 ? 1 : 0);      // ZSTD_cycleLog
-        if (cycleLog > cp.windowLog) cp.chainLog -= (cycleLog - cp.windowLog); }
-    if (cp.windowLog < 10) cp.windowLog = 10;
+    adjust_cparams(cp, srcSize);
+    if (ov) {
+        if (ov->windowLog) cp.windowLog = ov->windowLog;
+        if (ov->hashLog) cp.hashLog = ov->hashLog;
+        if (ov->chainLog) cp.chainLog = ov->chainLog;
+        if (ov->searchLog) cp.searchLog = ov->searchLog;
+        if (ov->minMatch) cp.minMatch = ov->minMatch;
+        if (ov->targetLength) cp.targetLength = ov->targetLength;
+        if (ov->strategy) cp.strategy = ov->strategy;
+        if (cp.strategy > S_btlazy2) return false;
+        adjust_cparams(cp, srcSize);
+        if (checkWindow && ((size_t)1 << cp.windowLog) < srcSize) return false;
+    }
     *out = cp;
     return true;
 }
@@ -2062,16 +2084,16 @@ ZB_HDN u32 export_sequences(const C& w, const Seq* in, u32 nbSeq, u32 lastLL, si
 //   parse_stage   match finding -> sequences (W.seq*), their count and the trailing literal run
 //   encode_stage  frame/block headers, literal gathering, Huffman + FSE entropy stage
 // Together they emit what ZSTD_compress2 would with dstCapacity = ZSTD_compressBound(srcSize).
-constexpr u32 FRAME_CHECKSUM = 1, FRAME_NO_CONTENT_SIZE = 2;      // frameFlags: ZSTD_c_checksumFlag = 1, ZSTD_c_contentSizeFlag = 0
+constexpr u32 FRAME_CHECKSUM = 1, FRAME_NO_CONTENT_SIZE = 2, FRAME_MAGICLESS = 4;      // frameFlags: ZSTD_c_checksumFlag = 1, ZSTD_c_contentSizeFlag = 0, ZSTD_c_format = ZSTD_f_zstd1_magicless
 
 // ONLY = 0: every parser is compiled in.  ONLY = S_dfast / S_fast: the caller guarantees that this level selects that
 // strategy for every input size, so the kernel holds a single cooperative parser (64 registers without spills; the
 // all-in-one instantiation needs ~1 KB of stack).
 template <class C, u32 ONLY = 0>
-ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t srcSize, int level, u32* nbSeqOut, u32* lastLLOut) {
+ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t srcSize, int level, u32* nbSeqOut, u32* lastLLOut, const CParams* ov = nullptr) {
     CParams cp;
     *nbSeqOut = PARSE_SKIPPED; *lastLLOut = 0;
-    if (!get_cparams(&cp, level, srcSize)) return ERR(E_parameter_unsupported);
+    if (!get_cparams(&cp, level, srcSize, ov)) return ERR(E_parameter_unsupported);
     if (ONLY != 0 && cp.strategy != ONLY) return ERR(E_GENERIC);
     if (srcSize < 7) return 0;
     {   // fresh tables: zero the used part (16-byte stores; the workspace is 16-byte aligned)
@@ -2109,24 +2131,26 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
 // `dst` must have room for compress_bound(srcSize) + 32 bytes.  Uniform return value.
 template <class C>
 ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level, u32 nbSeq, u32 lastLL,
-                           u32 frameFlags = 0) {
+                           u32 frameFlags = 0, const CParams* ov = nullptr) {
     CParams cp;
-    if (!get_cparams(&cp, level, srcSize)) return ERR(E_parameter_unsupported);
+    if (!get_cparams(&cp, level, srcSize, ov)) return ERR(E_parameter_unsupported);
     if (dstCapacity < 18) return ERR(E_dstSize_tooSmall);
     size_t pos = 0;
     // ZSTD_writeFrameHeader :4695-4743 (no dictionary): the pledged size is known in a one-shot call, so the window
     // covers the input and the frame is "single segment" whenever the content size is written
     bool const checksum = (frameFlags & FRAME_CHECKSUM) != 0, contentSize = !(frameFlags & FRAME_NO_CONTENT_SIZE);
     u32 const fcsCode = contentSize ? (srcSize >= 256) + (srcSize >= 65536 + 256) : 0;
+    u32 const mlen = (frameFlags & FRAME_MAGICLESS) ? 0u : 4u;        // the magic number is written for ZSTD_f_zstd1 only (:4716-4719)
     if (w.lane == 0) {
-        dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
-        dst[4] = (u8)((checksum ? 4 : 0) + (contentSize ? (1 << 5) : 0) + (fcsCode << 6));
-        if (!contentSize) dst[5] = (u8)((cp.windowLog - 10) << 3);
-        else if (fcsCode == 0) dst[5] = (u8)srcSize;
-        else if (fcsCode == 1) { u32 const v = (u32)srcSize - 256; dst[5] = (u8)v; dst[6] = (u8)(v >> 8); }
-        else { u32 const v = (u32)srcSize; dst[5] = (u8)v; dst[6] = (u8)(v >> 8); dst[7] = (u8)(v >> 16); dst[8] = (u8)(v >> 24); }
+        if (mlen) { dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD; }
+        u8* const h = dst + mlen;
+        h[0] = (u8)((checksum ? 4 : 0) + (contentSize ? (1 << 5) : 0) + (fcsCode << 6));
+        if (!contentSize) h[1] = (u8)((cp.windowLog - 10) << 3);
+        else if (fcsCode == 0) h[1] = (u8)srcSize;
+        else if (fcsCode == 1) { u32 const v = (u32)srcSize - 256; h[1] = (u8)v; h[2] = (u8)(v >> 8); }
+        else { u32 const v = (u32)srcSize; h[1] = (u8)v; h[2] = (u8)(v >> 8); h[3] = (u8)(v >> 16); h[4] = (u8)(v >> 24); }
     }
-    pos = 5 + (!contentSize ? 1 : fcsCode == 0 ? 1 : fcsCode == 1 ? 2 : 4);
+    pos = mlen + 1 + (!contentSize ? 1 : fcsCode == 0 ? 1 : fcsCode == 1 ? 2 : 4);
     // ZSTD_writeEpilogue :5344-5381: the low 32 bits of XXH64(content) follow the last block when asked for
     u32 const sumBytes = checksum ? 4 : 0;
     u32 sum = 0;
@@ -2191,11 +2215,12 @@ ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, 
 
 // both stages on one context (host instantiation, single-kernel use)
 template <class C>
-ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level, u32 frameFlags = 0) {
+ZB_HDN size_t compress_frame(const C& w, EncShared& S, const EncWork& W, u8* dst, size_t dstCapacity, const u8* src, size_t srcSize, int level, u32 frameFlags = 0,
+                             const CParams* ov = nullptr) {
     u32 nbSeq = 0, lastLL = 0;
-    size_t const r = parse_stage(w, W, src, srcSize, level, &nbSeq, &lastLL);
+    size_t const r = parse_stage(w, W, src, srcSize, level, &nbSeq, &lastLL, ov);
     if (isErr(r)) return r;
-    return encode_stage(w, S, W, dst, dstCapacity, src, srcSize, level, nbSeq, lastLL, frameFlags);
+    return encode_stage(w, S, W, dst, dstCapacity, src, srcSize, level, nbSeq, lastLL, frameFlags, ov);
 }
 
 }  // namespace zb

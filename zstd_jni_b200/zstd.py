@@ -26,6 +26,9 @@ ZSTD_c_compressionLevel = 100
 ZSTD_c_contentSizeFlag = 200
 ZSTD_c_checksumFlag = 201
 ZSTD_c_dictIDFlag = 202
+ZSTD_c_format = 10
+ZSTD_d_windowLogMax = 100
+ZSTD_d_format = 1000
 ZSTD_e_continue, ZSTD_e_flush, ZSTD_e_end = 0, 1, 2
 BLOCK = 131072
 
@@ -107,15 +110,38 @@ class Zstd:
             return ctx.decompressByteArray(dst, 0, len(dst), src, 0, len(src), raise_on_error=False)
 
     @staticmethod
-    def getFrameContentSize(src) -> int:                 # J/Zstd.java:getFrameContentSize ; -1 unknown, -2 error like the C API
+    def getFrameContentSize(src, magicless: bool = False) -> int:   # J/Zstd.java:729-739 ; -1 unknown, -2 error like the C API
         p, n, _k = _buf(src)
-        v = N.lib().ZSTD_getFrameContentSize(p, n)
+        if magicless:                                    # N/jni_zstd.c:32-40: header parse in the magicless format, 0 on any failure
+            fh = N.FrameHeader()
+            if N.lib().ZSTD_getFrameHeader_advanced(C.byref(fh), p, n, 1) != 0:
+                return 0
+            v = fh.frameContentSize
+        else:
+            v = N.lib().ZSTD_getFrameContentSize(p, n)
         return v if v < (1 << 63) else v - (1 << 64)
 
     @staticmethod
-    def decompressedSize(src) -> int:                    # deprecated Java name; 0 when unknown / error
-        v = Zstd.getFrameContentSize(src)
+    def decompressedSize(src, magicless: bool = False) -> int:      # J/Zstd.java:754-764 (deprecated name); 0 when unknown / error
+        v = Zstd.getFrameContentSize(src, magicless)
         return v if v >= 0 else 0
+
+    @staticmethod
+    def getDictIdFromFrame(src) -> int:                  # J/Zstd.java:getDictIdFromFrame -> N/jni_zstd.c:139 (0: none / undecodable)
+        p, n, _k = _buf(src)
+        return N.lib().ZSTD_getDictID_fromFrame(p, n)
+
+    @staticmethod
+    def getFrameHeader(src, magicless: bool = False) -> dict:
+        """ZSTD_getFrameHeader_advanced as a dict (not in J/Zstd.java; what N/jni_zstd.c:32-40 looks at)."""
+        p, n, _k = _buf(src)
+        fh = N.FrameHeader()
+        r = N.lib().ZSTD_getFrameHeader_advanced(C.byref(fh), p, n, 1 if magicless else 0)
+        if N.is_error(r):
+            raise ZstdException(N.error_code(r), N.lib().ZSTD_getErrorName(r).decode())
+        if r:
+            raise ZstdException(72, f"Src size is incorrect (header needs {r} bytes)")
+        return {k: getattr(fh, k) for k, _t in N.FrameHeader._fields_ if not k.startswith("_")}
 
     @staticmethod
     def findFrameCompressedSize(src) -> int:
@@ -195,6 +221,13 @@ class ZstdCompressCtx(_AutoClose):
     def setDictID(self, flag: bool):
         return self._set(ZSTD_c_dictIDFlag, int(flag))
 
+    def setMagicless(self, flag: bool):                  # :84-90 -> N/jni_zstd.c:362-363 (ZSTD_c_format)
+        return self._set(ZSTD_c_format, int(flag))
+
+    def getFrameProgression(self) -> dict:               # :477-480 -> N/jni_fast_zstd.c:373 (J/ZstdFrameProgression.java fields)
+        fp = N.lib().ZSTD_getFrameProgression(self._live())
+        return {k: getattr(fp, k) for k, _t in N.FrameProgression._fields_}
+
     def reset(self):
         N.lib().ZSTD_CCtx_reset(self._live(), 3)
 
@@ -233,6 +266,15 @@ class ZstdDecompressCtx(_AutoClose):
         if self._ptr is not None:
             N.lib().ZSTD_freeDCtx(self._ptr)
             self._ptr = None
+
+    def setMagicless(self, flag: bool):                  # J/ZstdDecompressCtx.java:54-60 -> N/jni_zstd.c:413-414 (ZSTD_d_format)
+        r = N.lib().ZSTD_DCtx_setParameter(self._live(), ZSTD_d_format, int(flag))
+        if N.is_error(r):
+            raise ZstdException(N.error_code(r), N.lib().ZSTD_getErrorName(r).decode())
+        return self
+
+    def reset(self):
+        N.lib().ZSTD_DCtx_reset(self._live(), 3)
 
     def decompressByteArray(self, dst: bytearray, dstOffset: int, dstSize: int, src, srcOffset: int, srcSize: int, raise_on_error=True) -> int:
         self._live()
@@ -480,6 +522,14 @@ class ZstdInputStream:
         self._pos = 0
         self._eof = False
         self._closed = False
+
+    def setLongMax(self, windowLogMax: int):              # J/ZstdInputStreamNoFinalizer.java:126-135 -> N/jni_zstd.c:403 (ZSTD_d_windowLogMax)
+        if self._closed:
+            raise IOError("Stream closed")
+        r = N.lib().ZSTD_DCtx_setParameter(self._z, ZSTD_d_windowLogMax, windowLogMax)
+        if N.is_error(r):
+            raise ZstdException(N.error_code(r), N.lib().ZSTD_getErrorName(r).decode())
+        return self
 
     def read(self, n: int = -1) -> bytes:
         if self._closed:
