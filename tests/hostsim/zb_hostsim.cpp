@@ -39,6 +39,39 @@ size_t zbh_compress_flags(void* dst, size_t dstCapacity, const void* src, size_t
     return r;
 }
 
+// explicit compression parameters (ZSTD_c_windowLog ... ZSTD_c_strategy; 0 = from the level): ov7 = {windowLog, chainLog, hashLog,
+// searchLog, minMatch, targetLength, strategy}.  emu != 0: both stages on the 32-lane emulator.
+size_t zbh_compress_params(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, unsigned flags, const unsigned* ov7, int emu) {
+    using namespace zb;
+    if (srcSize > BLOCKSIZE_MAX) return ERR(E_srcSize_wrong);
+    CParams ov = { ov7[0], ov7[1], ov7[2], ov7[3], ov7[4], ov7[5], ov7[6] };
+    EncShared* S = (EncShared*)calloc(1, sizeof(EncShared));
+    u8* wk = (u8*)calloc(1, enc_work_bytes() + 64);
+    EncWork W = enc_work_carve(wk);
+    size_t const bound = compress_bound(srcSize);
+    u8* slot = (u8*)calloc(1, bound + 64);
+    u8* in = (u8*)calloc(1, srcSize + 64);
+    memcpy(in + 16, src, srcSize);
+    size_t r;
+    if (emu) {
+        size_t results[32]; u32 nbSeqs[32], lastLLs[32];
+        run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = parse_stage(w, W, in + 16, srcSize, level, &nbSeqs[w.lane], &lastLLs[w.lane], &ov); });
+        r = results[0];
+        for (int i = 1; i < 32; i++) if (results[i] != r || nbSeqs[i] != nbSeqs[0] || lastLLs[i] != lastLLs[0]) r = ERR(E_GENERIC);
+        if (!isErr(r)) {
+            run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = encode_stage(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level, nbSeqs[0], lastLLs[0], flags, &ov); });
+            r = results[0];
+            for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);
+        }
+    } else {
+        WarpHost w;
+        r = compress_frame(w, *S, W, slot, bound < 18 ? 18 : bound, in + 16, srcSize, level, flags, &ov);
+    }
+    if (!isErr(r)) { if (r > dstCapacity) r = ERR(E_dstSize_tooSmall); else memcpy(dst, slot, r); }
+    free(S); free(wk); free(slot); free(in);
+    return r;
+}
+
 size_t zbh_decompress_format(void* dst, size_t dstCapacity, const void* src, size_t srcSize, unsigned magicless);
 size_t zbh_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize) { return zbh_decompress_format(dst, dstCapacity, src, srcSize, 0); }
 size_t zbh_decompress_format(void* dst, size_t dstCapacity, const void* src, size_t srcSize, unsigned magicless) {

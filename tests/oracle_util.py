@@ -82,6 +82,7 @@ def hostsim():
         ("zbe_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
         ("zbe_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         ("zbp_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("zbh_compress_params", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_uint), C.c_int]),
         ("zbh_generate_sequences", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int]),
     ])
     if L is None:
@@ -251,3 +252,36 @@ def hostsim_generate_sequences(data: bytes, level: int, emu: bool = False):
     out = np.zeros((cap, 4), dtype=np.uint32)
     n = hostsim().zbh_generate_sequences(out.ctypes.data, cap, data, len(data), level, 1 if emu else 0)
     return out[:n].copy() if n <= ERR_MAX else -((1 << 64) - n)
+
+
+# ---- explicit compression parameters (J/ZstdCompressCtx.setWindowLog ... setStrategy -> ZSTD_c_windowLog ... ZSTD_c_strategy)
+CPARAM_IDS = {"windowLog": 101, "hashLog": 102, "chainLog": 103, "searchLog": 104, "minMatch": 105, "targetLength": 106, "strategy": 107}
+CPARAM_ORDER = ("windowLog", "chainLog", "hashLog", "searchLog", "minMatch", "targetLength", "strategy")      # zb::CParams member order
+
+
+def ref_compress_params(data: bytes, level: int, params: dict, checksum: bool = False):
+    """The compiled reference: ZSTD_CCtx_setParameter for every explicit parameter, then ZSTD_compress2."""
+    R = ref()
+    cctx = R.ZSTD_createCCtx()
+    try:
+        R.ZSTD_CCtx_setParameter(cctx, 100, level)
+        if checksum:
+            R.ZSTD_CCtx_setParameter(cctx, 201, 1)
+        for k, v in params.items():
+            r = R.ZSTD_CCtx_setParameter(cctx, CPARAM_IDS[k], v)
+            if r > ERR_MAX:
+                return -((1 << 64) - r)
+        cap = len(data) + (len(data) >> 8) + 1024
+        out = C.create_string_buffer(cap)
+        n = R.ZSTD_compress2(cctx, out, cap, data, len(data))
+        return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
+    finally:
+        R.ZSTD_freeCCtx(cctx)
+
+
+def hostsim_compress_params(data: bytes, level: int, params: dict, checksum: bool = False, emu: bool = False):
+    ov = (C.c_uint * 7)(*[int(params.get(k, 0)) for k in CPARAM_ORDER])
+    cap = len(data) + (len(data) >> 8) + 1024
+    out = C.create_string_buffer(cap)
+    n = hostsim().zbh_compress_params(out, cap, data, len(data), level, 1 if checksum else 0, ov, 1 if emu else 0)
+    return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)

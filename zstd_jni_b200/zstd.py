@@ -221,6 +221,29 @@ class ZstdCompressCtx(_AutoClose):
     def setDictID(self, flag: bool):
         return self._set(ZSTD_c_dictIDFlag, int(flag))
 
+    # explicit compression parameters (J/ZstdCompressCtx.java setWindowLog ... setStrategy -> N/jni_fast_zstd.c / N/jni_zstd.c
+    # setCompression*): applied over the level's row like the reference; 0 restores the level's value
+    def setWindowLog(self, v: int):
+        return self._set(101, v)
+
+    def setHashLog(self, v: int):
+        return self._set(102, v)
+
+    def setChainLog(self, v: int):
+        return self._set(103, v)
+
+    def setSearchLog(self, v: int):
+        return self._set(104, v)
+
+    def setMinMatch(self, v: int):
+        return self._set(105, v)
+
+    def setTargetLength(self, v: int):
+        return self._set(106, v)
+
+    def setStrategy(self, v: int):
+        return self._set(107, v)
+
     def setMagicless(self, flag: bool):                  # :84-90 -> N/jni_zstd.c:362-363 (ZSTD_c_format)
         return self._set(ZSTD_c_format, int(flag))
 
