@@ -29,4 +29,17 @@ with ZstdCompressCtx() as c:
     z = c.compress(chunks[0]); assert Zstd.decompress(z, len(chunks[0])) == chunks[0]
     c.setMultiFrame(True)
     big = b"".join(chunks[:3]); z = c.compress(big); assert Zstd.decompress(z, len(big)) == big
+# r4 additions: sequence export, magicless frames, explicit parameters
+with ZstdBatchContext(0) as b:
+    seqs = b.generateSequences(chunks[:6] + [chunks[9]], 3)
+    print("sequences:", [s.shape[0] for s in seqs], flush=True)
+    b.setOption("magicless", 1)
+    frames = b.compressBatch(chunks[:4] + [b""], 3)
+    assert b.decompressBatch(frames, [len(c) for c in chunks[:4]] + [0]) == chunks[:4] + [b""]
+    b.setOption("magicless", 0)
+    for k, v in (("c_hashLog", 10), ("c_chainLog", 9), ("c_minMatch", 6), ("c_strategy", 4), ("c_searchLog", 6)):
+        b.setOption(k, v)
+    frames = b.compressBatch(chunks[:10], 3)
+    assert b.decompressBatch(frames, [len(c) for c in chunks[:10]]) == chunks[:10]
+    print("cparams ok", sum(map(len, frames)), flush=True)
 print("sanitize script done")
