@@ -193,13 +193,29 @@ ZSTDB200_API size_t zstdb200_compress_batch(zstdb200_ctx* ctx, int level, size_t
 ZSTDB200_API size_t zstdb200_decompress_batch(zstdb200_ctx* ctx, size_t n, const void* const* src, const size_t* srcSize,
                                               void* const* dst, const size_t* dstCapacity, size_t* dstSize);
 
+/* ---- entry points of features that are not built, kept here because they take THIS library's contexts (see zb_capi.cu): dictionaries
+ * (N/jni_zstd.c:271-346, N/jni_fast_zstd.c:133-250,325-362,673-710) and foreign sequence producers (N/jni_zstd.c:337-346).  A non-empty
+ * dictionary / non-NULL CDict or DDict is refused with ZSTD_error_parameter_unsupported, clearing calls succeed; after
+ * ZSTD_registerSequenceProducer(cctx, state, fn != NULL) compressions of that context report parameter_unsupported until it is cleared. */
+typedef struct ZSTD_CDict_s ZSTD_CDict;
+typedef struct ZSTD_DDict_s ZSTD_DDict;
+typedef struct { unsigned int offset; unsigned int litLength; unsigned int matchLength; unsigned int rep; } ZSTD_Sequence;     /* N/zstd.h:1315-1350 */
+typedef size_t (*ZSTD_sequenceProducer_F)(void* sequenceProducerState, ZSTD_Sequence* outSeqs, size_t outSeqsCapacity, const void* src, size_t srcSize,
+                                          const void* dict, size_t dictSize, int compressionLevel, size_t windowSize);       /* N/zstd.h:2930-2936 */
+ZSTDB200_API size_t ZSTD_CCtx_loadDictionary(ZSTD_CCtx* cctx, const void* dict, size_t dictSize);
+ZSTDB200_API size_t ZSTD_CCtx_refCDict(ZSTD_CCtx* cctx, const ZSTD_CDict* cdict);
+ZSTDB200_API size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* dctx, const void* dict, size_t dictSize);
+ZSTDB200_API size_t ZSTD_DCtx_refDDict(ZSTD_DCtx* dctx, const ZSTD_DDict* ddict);
+ZSTDB200_API size_t ZSTD_compress_usingCDict(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize, const ZSTD_CDict* cdict);
+ZSTDB200_API size_t ZSTD_decompress_usingDDict(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize, const ZSTD_DDict* ddict);
+ZSTDB200_API void ZSTD_registerSequenceProducer(ZSTD_CCtx* cctx, void* sequenceProducerState, ZSTD_sequenceProducer_F sequenceProducer);
+
 /* ---- sequences: the GPU match finder behind the reference's sequence-level plug points
  * ZSTD_Sequence is N/zstd.h:1315-1350.  zstdb200_generate_sequences is ZSTD_generateSequences
  * (N/compress/zstd_compress.c:3520-3553) for n independent blocks of <= 128 KB: block i yields the records the reference
  * writes for a one-shot input of that size at `level` -- its sequences with raw offsets and `rep`, then the block
  * delimiter {0, last literals, 0, 0}.  nbSeqs[i] = number of records or an error code (capacity too small:
  * dstSize_tooSmall; srcSize < 7: sequenceProducer_failed and an empty block: 0 records, as in the reference). */
-typedef struct { unsigned int offset; unsigned int litLength; unsigned int matchLength; unsigned int rep; } ZSTD_Sequence;
 ZSTDB200_API size_t zstdb200_generate_sequences(zstdb200_ctx* ctx, int level, size_t n, const void* const* src, const size_t* srcSize,
                                                 ZSTD_Sequence* const* outSeqs, const size_t* outSeqsCapacity, size_t* nbSeqs);
 /* A block-level external sequence producer of type ZSTD_sequenceProducer_F (N/zstd.h:2820-2900), to be registered with

@@ -13,7 +13,7 @@ h_src = torch.from_numpy(data.reshape(-1)).pin_memory()
 stride = (L.ZSTD_compressBound(CH) + 32 + 63) // 64 * 64
 h_stream = torch.empty(n * stride, dtype=torch.uint8).pin_memory(); h_back = torch.empty(n * CH, dtype=torch.uint8).pin_memory()
 fsz = (C.c_size_t * n)(); tot = C.c_size_t(0); dsz = (C.c_size_t * n)()
-for slices, dslices in ((2, 2), (2, 3), (2, 4), (2, 6), (3, 4)):
+for slices, dslices in ((2, 2), (1, 1), (2, 1), (1, 2)):
     ctx.setOption("host_slices", slices); ctx.setOption("host_slices_dec", dslices)
     ts = []
     for rep in range(4):

@@ -128,6 +128,30 @@ def test_full_size_config_properties(ctx):
     assert oracle_decompress(stream[: offs[k]].tobytes(), k * 131072) == data[:k].tobytes()
 
 
+def test_mixed_level_frame_batches(ctx):
+    """configs[3] shape at a CI-sized scale: pre-built frames of mixed entropy (levels cycling 1 / 3 / 9, ragged sizes, a sample checked
+    against the oracle), decoded in batches of several sizes; every batch must regenerate exactly its chunks."""
+    from zstd_jni_b200 import corpus
+    rng = np.random.default_rng(21)
+    n = 600
+    chunks = [corpus.chunk(j)[: (131072 if j % 5 else int(rng.integers(1, 131072)))].tobytes() for j in range(n)]
+    frames = [None] * n
+    for k, level in enumerate((1, 3, 9)):
+        idx = list(range(k, n, 3))
+        for j, f in zip(idx, ctx.compressBatch([chunks[j] for j in idx], level)):
+            frames[j] = f
+        for j in idx[:6]:
+            assert frames[j] == oracle_compress(chunks[j], level), (j, level)
+    order = rng.permutation(n)
+    for batch in (64, 512, n):
+        for lo in range(0, n, batch):
+            sel = order[lo:lo + batch]
+            stream = np.frombuffer(b"".join(frames[j] for j in sel), dtype=np.uint8)
+            out, osz = ctx.decompressFrames(stream, [len(frames[j]) for j in sel], [len(chunks[j]) for j in sel])
+            assert [int(x) for x in osz] == [len(chunks[j]) for j in sel]
+            assert out.tobytes() == b"".join(chunks[j] for j in sel), (batch, lo)
+
+
 def test_staged_and_fused_decoders_agree(ctx):
     """The staged batch decoder (default) and the fused kernel must return the same bytes and the same
     error codes on a mixed bag: valid single-block frames, multi-block streams, corrupted frames."""

@@ -64,6 +64,9 @@ def jni():
         dctxInit = sig("ZstdDecompressCtx_init", jl)
         dctxFree = sig("ZstdDecompressCtx_free", None, jl)
         dctxDecompressByteArray = sig("ZstdDecompressCtx_decompressByteArray0", jl, jl, vp, ji, ji, vp, ji, ji)
+        loadDictCompress = sig("Zstd_loadDictCompress", ji, jl, vp, ji)
+        loadDictDecompress = sig("Zstd_loadDictDecompress", ji, jl, vp, ji)
+        registerSequenceProducer = sig("Zstd_registerSequenceProducer", None, jl, jl, jl)
         setMagicless = sig("Zstd_setCompressionMagicless", ji, jl, jb)
         setHashLog = sig("Zstd_setCompressionHashLog", ji, jl, ji)
 
@@ -129,6 +132,36 @@ def test_jni_host_side_entry_points(jni):
     assert _err(J.setHashLog(J.env, None, c, 31)) == 42                                     # out of bounds like the reference
     assert J.cctxReset(J.env, None, c) == 0
     J.cctxFree(J.env, None, c)
+
+
+def test_jni_unbuilt_features_refuse_loudly(jni):
+    """Dictionaries and foreign sequence producers are not built.  Their context-taking entry points are exported by libzstdb200
+    (the contexts are this library's objects; a CPU libzstd behind must never see them) and refuse with parameter_unsupported."""
+    import subprocess
+    J = jni
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", str(JNI_LIB)], capture_output=True, text=True, check=True).stdout.split()
+    from zstd_jni_b200 import _native as N
+    ours = subprocess.run(["nm", "-D", "--defined-only", str(N.LIB_PATH)], capture_output=True, text=True, check=True).stdout.split()
+    cold = sorted(x for x in undefined if x.startswith(("ZSTD_", "ZDICT_")) and x not in ours)
+    # what is left to the CPU library takes no ZSTD_CCtx / ZSTD_DCtx: dictionary objects and the dictionary trainer
+    assert cold == ["ZDICT_trainFromBuffer", "ZDICT_trainFromBuffer_legacy", "ZSTD_createCDict", "ZSTD_createCDict_byReference", "ZSTD_createDDict",
+                    "ZSTD_createDDict_byReference", "ZSTD_freeCDict", "ZSTD_freeDDict", "ZSTD_getDictID_fromDict"], cold
+    c, d = J.cctxInit(J.env, None), J.dctxInit(J.env, None)
+    a = J.array(b"a dictionary of sorts " * 20)
+    dst = J.array(size=1000)
+    src = J.array(b"hello hello hello hello hello hello")
+    try:
+        assert _err(J.loadDictCompress(J.env, None, c, a, 440)) == 40 and _err(J.loadDictDecompress(J.env, None, d, a, 440)) == 40
+        assert J.loadDictCompress(J.env, None, c, a, 0) == 0                              # clearing the dictionary is fine
+        J.registerSequenceProducer(J.env, None, c, 0, 0x1234)                           # a foreign match finder would bypass the GPU parsers
+        assert _err(J.cctxCompressByteArray(J.env, None, c, dst, 0, 1000, src, 0, 35)) == 40
+        J.registerSequenceProducer(J.env, None, c, 0, 0)
+        assert _err(J.cctxCompressByteArray(J.env, None, c, dst, 0, 1000, src, 0, 35)) in (0, 1)      # accepted again (GENERIC without a device)
+    finally:
+        for x in (a, dst, src):
+            J.harness.jh_free(x)
+        J.cctxFree(J.env, None, c)
+        J.dctxFree(J.env, None, d)
 
 
 def test_jni_compute_entry_points_fail_loudly_without_a_device(jni):
