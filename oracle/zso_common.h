@@ -33,6 +33,7 @@ enum {
     ZSO_error_checksum_wrong = 22,
     ZSO_error_literals_headerWrong = 24,
     ZSO_error_dictionary_corrupted = 30,
+    ZSO_error_dictionary_wrong = 32,
     ZSO_error_parameter_unsupported = 40,
     ZSO_error_tableLog_tooLarge = 44,
     ZSO_error_maxSymbolValue_tooLarge = 46,

@@ -534,7 +534,7 @@ uint64_t zso_xxh64(const void* data, size_t len, uint64_t seed) {
 }
 
 /* ------------------------------------------------------------ frame layer */
-typedef struct { size_t headerSize; uint64_t contentSize; uint64_t windowSize; size_t blockSizeMax; int checksum; int skippable; uint32_t skipLen; int hasContentSize; } zso_fh;
+typedef struct { size_t headerSize; uint64_t contentSize; uint64_t windowSize; size_t blockSizeMax; int checksum; int skippable; uint32_t skipLen; int hasContentSize; uint32_t dictID; } zso_fh;
 
 /* ZSTD_getFrameHeader_advanced, N/decompress/zstd_decompress.c:447-551. returns 0, or wanted size, or error */
 static size_t read_frame_header(zso_fh* fh, const uint8_t* src, size_t srcSize) {
@@ -570,6 +570,7 @@ static size_t read_frame_header(zso_fh* fh, const uint8_t* src, size_t srcSize) 
             if (windowLog > 31) return ZSO_ERROR(frameParameter_windowTooLarge);
             fh->windowSize = 1ULL << windowLog; fh->windowSize += (fh->windowSize >> 3) * (wl & 7);
         }
+        {   unsigned i; for (i = 0; i < did[dictID]; i++) fh->dictID |= (uint32_t)src[pos + i] << (8 * i); }     /* :508-516 */
         pos += did[dictID];
         fh->hasContentSize = 1;
         switch (fcsID) {
@@ -625,6 +626,8 @@ static size_t decode_frame(zso_dctx* d, uint8_t* dst, size_t dstCapacity, const 
         if (zso_isError(r)) return r;
         if (r > 0) return ZSO_ERROR(srcSize_wrong);
         if (left < fh.headerSize + 3) return ZSO_ERROR(srcSize_wrong);
+        /* ZSTD_decodeFrameHeader :706-707: the frame names a dictionary, none is loaded */
+        if (fh.dictID != 0) return ZSO_ERROR(dictionary_wrong);
         ip += fh.headerSize; left -= fh.headerSize;
     }
     d->rep[0] = 1; d->rep[1] = 4; d->rep[2] = 8; d->litEntropy = d->fseEntropy = 0;

@@ -60,6 +60,21 @@ def test_magicless_pins_against_reference():
             assert hostsim_compress_flags(d, 3, ck, cs, magicless=True) == ref_compress_flags(d, 3, ck, cs, True)
 
 
+def test_frames_naming_a_dictionary_are_refused_like_the_reference():
+    """A frame whose header carries a non-zero dictionary ID cannot be decoded without that dictionary: dictionary_wrong (32), from the fused
+    decoder, the staged decoder (which hands such frames over) and the emulated warp; a dictID field of 0 is decoded normally."""
+    from tests.oracle_util import emu_decompress, hostsim_decompress, staged_decompress
+    data = regenerate_input({"kind": "corpus", "index": 1, "size": 20000})
+    z = oracle_compress_flags(data, 3)
+    named = z[:4] + bytes([z[4] | 1]) + b"\x07" + z[5:]
+    zero_id = z[:4] + bytes([z[4] | 2]) + b"\x00\x00" + z[5:]
+    for dec in (hostsim_decompress, emu_decompress, staged_decompress):
+        assert dec(named, 20000) == -32 and dec(zero_id, 20000) == data
+    if ref() is not None:
+        from tests.oracle_util import ref_decompress
+        assert ref_decompress(named, 20000) == -32 and ref_decompress(zero_id, 20000) == data
+
+
 def _header_fields(h):
     return [h.frameContentSize, h.windowSize, h.blockSizeMax, h.frameType, h.headerSize, h.dictID, h.checksumFlag]
 

@@ -160,3 +160,14 @@ def test_randomised_levels_and_sizes():
             assert exp == ref_compress(data, level), (it, n, level)
         got = hostsim_compress(data, level) if it % 2 == 0 else emu_compress(data, level)
         assert got == exp, (it, n, level)
+
+
+def test_decoders_never_write_outside_their_destination(tmp_path):
+    """tests/hostsim/canary_fuzz.cpp: corrupted and intact frames through the fused, emulated-warp and staged decoders; the destination is
+    fenced by canaries on both sides (on the GPU the neighbours are other frames' outputs)."""
+    import subprocess
+    src = Path(__file__).parent / "hostsim" / "canary_fuzz.cpp"
+    exe = tmp_path / "canary_fuzz"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wno-unused-function", str(src), "-o", str(exe)], check=True, cwd=str(src.parent))
+    out = subprocess.run([str(exe), "11", "150"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "canary violations 0" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

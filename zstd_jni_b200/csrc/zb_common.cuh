@@ -32,7 +32,7 @@ typedef int16_t i16;
 // ---- error convention: (size_t)-code, N/common/error_private.h:49-54
 enum : int {
     E_GENERIC = 1, E_prefix_unknown = 10, E_frameParameter_unsupported = 14, E_frameParameter_windowTooLarge = 16,
-    E_corruption_detected = 20, E_checksum_wrong = 22, E_literals_headerWrong = 24, E_dictionary_corrupted = 30,
+    E_corruption_detected = 20, E_checksum_wrong = 22, E_literals_headerWrong = 24, E_dictionary_corrupted = 30, E_dictionary_wrong = 32,
     E_parameter_unsupported = 40, E_parameter_outOfBound = 42, E_tableLog_tooLarge = 44, E_maxSymbolValue_tooLarge = 46,
     E_maxSymbolValue_tooSmall = 48, E_stage_wrong = 60, E_init_missing = 62, E_memory_allocation = 64, E_workSpace_tooSmall = 66,
     E_dstSize_tooSmall = 70, E_srcSize_wrong = 72, E_dstBuffer_null = 74, E_sequenceProducer_failed = 106, E_externalSequences_invalid = 107,

@@ -626,6 +626,8 @@ ZB_HDN size_t decompress_item(const C& w, DecShared& S, const u8* src, size_t sr
             if (isErr(r)) return (more && r == ERR(E_prefix_unknown)) ? ERR(E_srcSize_wrong) : r;
             if (r > 0) return ERR(E_srcSize_wrong);
             if (srcSize < fh.headerSize + 3) return ERR(E_srcSize_wrong);
+            // the frame names a dictionary and none can be loaded here (ZSTD_decodeFrameHeader, N/decompress/zstd_decompress.c:706-707)
+            if (fh.dictID != 0) return ERR(E_dictionary_wrong);
         }
         const u8* ip = src + fh.headerSize; size_t left = srcSize - fh.headerSize;
         if (w.lane == 0) { S.rep[0] = 1; S.rep[1] = 4; S.rep[2] = 8; S.litEntropy = 0; S.fseEntropy = 0; }

@@ -56,7 +56,7 @@ ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize,
         if (load32(src) != MAGIC) break;
         FrameHeader fh;
         size_t const r = read_frame_header(&fh, src, srcSize);
-        if (r != 0 || fh.skippable || fh.checksum || !fh.hasContentSize) break;
+        if (r != 0 || fh.skippable || fh.checksum || !fh.hasContentSize || fh.dictID != 0) break;
         if (fh.contentSize > BLOCKSIZE_MAX) break;
         if (srcSize < fh.headerSize + 3) break;
         const u8* const bp = src + fh.headerSize;
