@@ -622,6 +622,11 @@ static size_t decode_frame(zso_dctx* d, uint8_t* dst, size_t dstCapacity, const 
     if (left < 6 + 3) {   /* ZSTD_FRAMEHEADERSIZE_MIN(6) + blockHeader */
         return ZSO_ERROR(srcSize_wrong);
     }
+    {   /* :972-979: header size from the descriptor byte alone; too short for header + block header => srcSize_wrong before validation */
+        static const uint8_t didSz[4] = { 0, 1, 2, 4 }, fcsSz[4] = { 0, 2, 4, 8 };
+        uint8_t const fhd = ip[4]; unsigned const single = (fhd >> 5) & 1;
+        size_t const hs0 = 5 + !single + didSz[fhd & 3] + fcsSz[fhd >> 6] + (single && !(fhd >> 6));
+        if (left < hs0 + 3) return ZSO_ERROR(srcSize_wrong); }
     {   size_t r = read_frame_header(&fh, ip, left);
         if (zso_isError(r)) return r;
         if (r > 0) return ZSO_ERROR(srcSize_wrong);

@@ -621,6 +621,11 @@ ZB_HDN size_t decompress_item(const C& w, DecShared& S, const u8* src, size_t sr
         }
         // ---- one frame
         if (srcSize < (magicless ? 2u : 6u) + 3) return ERR(E_srcSize_wrong);     // ZSTD_FRAMEHEADERSIZE_MIN(format) + block header
+        {   // ZSTD_decompressFrame :972-979: the header size comes from the descriptor byte alone, and a frame too short for header + one
+            // block header is srcSize_wrong before the header itself is validated (magic, reserved bit, window)
+            u32 const fhd = src[magicless ? 0 : 4], did = fhd & 3, single = (fhd >> 5) & 1, fcs = fhd >> 6;
+            size_t const hs = (magicless ? 1u : 5u) + !single + (did == 3 ? 4 : did) + (fcs == 0 ? 0 : (1u << fcs)) + (single && !fcs);
+            if (srcSize < hs + 3) return ERR(E_srcSize_wrong); }
         FrameHeader fh;
         {   size_t const r = read_frame_header(&fh, src, srcSize, magicless);
             if (isErr(r)) return (more && r == ERR(E_prefix_unknown)) ? ERR(E_srcSize_wrong) : r;
