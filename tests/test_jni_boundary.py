@@ -134,6 +134,18 @@ def test_jni_host_side_entry_points(jni):
     J.cctxFree(J.env, None, c)
 
 
+def test_python_mirror_constants_equal_the_glue_s(jni):
+    """J/Zstd.java's constant getters: the Python mirror must return what the reference's glue (compiled from the reference's headers) returns."""
+    from zstd_jni_b200.zstd import Zstd
+    L = C.CDLL(str(JNI_LIB))
+    for name in list(Zstd._ERR) + ["magicNumber", "blockSizeMax", "windowLogMin", "windowLogMax", "chainLogMin", "chainLogMax", "hashLogMin", "hashLogMax",
+                                   "searchLogMin", "searchLogMax"]:      # searchLengthMin / Max are declared in J/Zstd.java:1108-1109 but have no native in N/jni_zstd.c
+        f = getattr(L, P + "Zstd_" + name)
+        f.restype = jl if name.startswith("err") else ji
+        f.argtypes = [vp, vp]
+        assert f(jni.env, None) == getattr(Zstd, name)(), name
+
+
 def test_jni_unbuilt_features_refuse_loudly(jni):
     """Dictionaries and foreign sequence producers are not built.  Their context-taking entry points are exported by libzstdb200
     (the contexts are this library's objects; a CPU libzstd behind must never see them) and refuse with parameter_unsupported."""

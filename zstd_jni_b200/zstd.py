@@ -58,6 +58,13 @@ def _buf(b) -> tuple[C.c_void_p, int, object]:
 class Zstd:
     """Static facade, J/Zstd.java."""
 
+    # J/Zstd.java:929-951 (errNoError ... errDstBufferNull): the ZSTD_ErrorCode enum of N/zstd_errors.h
+    _ERR = {"errNoError": 0, "errGeneric": 1, "errPrefixUnknown": 10, "errVersionUnsupported": 12, "errFrameParameterUnsupported": 14,
+            "errFrameParameterWindowTooLarge": 16, "errCorruptionDetected": 20, "errChecksumWrong": 22, "errDictionaryCorrupted": 30,
+            "errDictionaryWrong": 32, "errDictionaryCreationFailed": 34, "errParameterUnsupported": 40, "errParameterOutOfBound": 42,
+            "errTableLogTooLarge": 44, "errMaxSymbolValueTooLarge": 46, "errMaxSymbolValueTooSmall": 48, "errStageWrong": 60, "errInitMissing": 62,
+            "errMemoryAllocation": 64, "errWorkSpaceTooSmall": 66, "errDstSizeTooSmall": 70, "errSrcSizeWrong": 72, "errDstBufferNull": 74}
+
     @staticmethod
     def isError(code: int) -> bool:                      # J/Zstd.java:isError
         return bool(N.lib().ZSTD_isError(code & ((1 << 64) - 1)))
@@ -150,6 +157,55 @@ class Zstd:
         if N.is_error(r):
             raise ZstdException(N.error_code(r), N.lib().ZSTD_getErrorName(r).decode())
         return r
+
+    # ---- constants of the format / parameter space (J/Zstd.java:929-951,1099-1110 -> N/jni_zstd.c:573-667: header macros and error enum)
+    @staticmethod
+    def magicNumber() -> int:
+        return 0xFD2FB528 - (1 << 32)                    # a Java int
+
+    @staticmethod
+    def blockSizeMax() -> int:
+        return BLOCK
+
+    @staticmethod
+    def windowLogMin() -> int:
+        return 10
+
+    @staticmethod
+    def windowLogMax() -> int:
+        return 31
+
+    @staticmethod
+    def chainLogMin() -> int:
+        return 6
+
+    @staticmethod
+    def chainLogMax() -> int:
+        return 30
+
+    @staticmethod
+    def hashLogMin() -> int:
+        return 6
+
+    @staticmethod
+    def hashLogMax() -> int:
+        return 30
+
+    @staticmethod
+    def searchLogMin() -> int:
+        return 1
+
+    @staticmethod
+    def searchLogMax() -> int:
+        return 30
+
+    @staticmethod
+    def searchLengthMin() -> int:                        # ZSTD_MINMATCH_MIN (declared in J/Zstd.java:1108 without a native in N/jni_zstd.c)
+        return 3
+
+    @staticmethod
+    def searchLengthMax() -> int:
+        return 7
 
     # ---- batch entry points (new surface)
     @staticmethod
@@ -472,6 +528,10 @@ class B200SequenceProducer:
 
     def freeState(self, statePointer: int) -> None:
         N.lib().zstdb200_freeSequenceProducerState(statePointer)
+
+
+for _name, _code in Zstd._ERR.items():
+    setattr(Zstd, _name, staticmethod(lambda _c=_code: _c))
 
 
 class ZstdOutputStream:
