@@ -36,7 +36,7 @@ def test_hostsim_cparams_match_golden():
 
 
 def test_emulated_warp_cparams_match_golden():
-    for e in GOLDEN[::4]:
+    for e in GOLDEN[::7]:
         _check(e, hostsim_compress_params(regenerate_input(e["input"]), e["level"], e["params"], emu=True))
 
 
