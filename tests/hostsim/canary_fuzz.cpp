@@ -45,6 +45,7 @@ int main(int argc, char** argv) {
     DecShared* S = (DecShared*)calloc(1, sizeof(DecShared));
     u8* scratch = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
     u8* lit = (u8*)calloc(1, BLOCKSIZE_MAX + 64); u16* huf = (u16*)calloc(FAST_HUF_ENTRIES, 2); u32* fse = (u32*)calloc(FAST_FSE_ENTRIES, 4); u64* seqs = (u64*)calloc(FAST_MAXS + 8, 8);
+    ExecShared* X = (ExecShared*)aligned_alloc(16, (sizeof(ExecShared) + 15) / 16 * 16);
     long bad = 0, ok = 0, errs = 0;
     for (int it = 0; it < iters; it++) {
         F const& f = frames[rng() % frames.size()];
@@ -74,7 +75,7 @@ int main(int argc, char** argv) {
                 for (int k = 0; k < 4; k++) dec_huf(&d, k, blk, huf, lit);
                 dec_seq(&d, blk, fse, &h_tables, seqs);
                 size_t results[32];
-                run_warp<32>([&](const WarpEmuT<32>& w2) { results[w2.lane] = dec_exec(w2, &d, in + 16, lit, seqs, out + PRE, cap); });
+                run_warp<32>([&](const WarpEmuT<32>& w2) { results[w2.lane] = dec_exec(w2, *X, &d, in + 16, lit, seqs, out + PRE, cap); });
                 r = results[0];
             }
             for (size_t i = 0; i < PRE; i++) if (out[i] != 0xA5) { bad++; printf("seed %u it %d variant %d: write BEFORE dst at -%zu\n", seed, it, variant, PRE - i); break; }

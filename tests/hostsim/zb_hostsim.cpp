@@ -2,6 +2,7 @@
 // templates in zstd_jni_b200/csrc/*.cuh.  It lets `pytest -m "not gpu"` exercise the
 // very source the CUDA kernels are built from on a machine without a GPU.  It is never
 // loaded by the product path (zstd_jni_b200/lib/libzstdb200.so has no CPU fallback).
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include "../../zstd_jni_b200/csrc/zb_decode.cuh"
@@ -143,6 +144,7 @@ size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     u8* lit = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
     u16* huf = (u16*)calloc(FAST_HUF_ENTRIES, 2);
     u32* fse = (u32*)calloc(FAST_FSE_ENTRIES, 4);
+    ExecShared* X = (ExecShared*)aligned_alloc(16, (sizeof(ExecShared) + 15) / 16 * 16);
     u64* seqs = (u64*)calloc(FAST_MAXS + 8, 8);
     DecDesc d;
     size_t r;
@@ -156,15 +158,16 @@ size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
         const u8* blk = in + 16 + d.blockOff;
         for (int k = 0; k < 4; k++) dec_huf(&d, k, blk, huf, lit);
         dec_seq(&d, blk, fse, &h_tables, seqs);
+        if (getenv("ZB_DEBUG_STAGES")) fprintf(stderr, "mode %u stA1 %u stB %u stA2 %u stC %u nbSeq %u litMode %u litSize %u hufLog %u nStreams %u seqBits %u logs %u %u %u\n", d.mode, d.stA1, d.stB, d.stA2, d.stC, d.nbSeq, d.litMode, d.litSize, d.hufLog, d.nStreams, d.seqBits, d.logLL, d.logOF, d.logML);
         if (emu) {
             size_t results[32];
-            run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = dec_exec(w, &d, in + 16, lit, seqs, out + 16, dstCapacity); });
+            run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = dec_exec(w, *X, &d, in + 16, lit, seqs, out + 16, dstCapacity); });
             r = results[0];
             for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);
-        } else { WarpHost w; r = dec_exec(w, &d, in + 16, lit, seqs, out + 16, dstCapacity); }
+        } else { WarpHost w; r = dec_exec(w, *X, &d, in + 16, lit, seqs, out + 16, dstCapacity); }
     }
     if (!isErr(r)) memcpy(dst, out + 16, r);
-    free(S); free(in); free(out); free(lit); free(huf); free(fse); free(seqs);
+    free(S); free(in); free(out); free(lit); free(huf); free(fse); free(seqs); free(X);
     return r;
 }
 

@@ -1,20 +1,25 @@
-// zb_decode_fast.cuh -- staged ("transposed") decoder for batches of single-block frames.
+// zb_decode_fast.cuh -- staged ("transposed") decoder for batches of single-block frames, second generation.
 //
 // In a batch of thousands of frames the serial chains of the format (Huffman streams, the three coupled FSE
-// states of the sequence stream) are the critical path.  The fused kernel (zb_decode.cuh) walks them with one
-// lane of a warp while 31 lanes wait.  This pipeline gives every chain its own *thread* and runs all of them
-// at once, then executes the sequences with whole warps:
+// states of the sequence stream) are the critical path.  This pipeline gives every chain its own *thread*, runs
+// all of them at once next to each other, and then executes the sequences with whole warps:
 //
-//   A  dec_prepare   warp / frame    frame + block + section headers, Huffman and FSE decode tables -> HBM
-//   B  dec_huf       thread / stream 4 x n threads, each decodes one Huffman stream into the literal buffer
-//   C  dec_seq       thread / frame  sequence bitstream -> (litLength, matchLength, offset) packed in 8 bytes
-//   D  dec_exec      warp / frame    32 sequences per step: positions by prefix sums, literal runs and
-//                                    independent matches copied lane-per-sequence, dependent ones in waves
+//   A  dec_prepare   warp / frame    frame + block + section headers, Huffman and FSE decode tables -> HBM,
+//                                    bit lengths of every backward stream
+//   B  HufChain      thread / stream 4 x n chains, each decodes one Huffman stream into the literal buffer   } one persistent
+//   C  SeqChain      thread / frame  sequence bitstream -> (litLength, matchLength, offset) packed in 8 B   } kernel (k_dec_chains)
+//   D  dec_exec      warp / frame    "byte gather": every output byte finds its sequence and its source byte,
+//                                    128 output bytes per round, no ordering between the lanes
+//
+// Both chain kinds read their bitstream through a `word source`: on the GPU a per-lane ring in shared memory that
+// 16-byte asynchronous copies (cp.async) keep several hundred bytes ahead of the reader, on the host (tests) the
+// plain byte array.  Their tables sit in shared memory, brought in by one bulk asynchronous copy
+// (cp.async.bulk + mbarrier) per table when a lane takes its next frame.
 //
 // An item is eligible when it is exactly one frame with one (last) block, carries its content size and no
-// checksum; everything else (multi-block, multi-frame, skippable, checksummed, > MAXS sequences) is left to
-// the fused kernel.  Results -- including the error code of corrupted input -- are identical to the fused
-// path: the stage statuses are combined in the order the fused decoder would have met the errors.
+// checksum; everything else (multi-block, multi-frame, skippable, checksummed, > MAXS sequences, 2^12-cell Huffman
+// tables) is left to the fused kernel.  Results -- including the error code of corrupted input -- are identical to
+// the fused path: the stage statuses are combined in the order the fused decoder would have met the errors.
 //
 // Reference behaviour reproduced: see zb_decode.cuh (N/decompress/zstd_decompress_block.c:134-340,695-775,
 // 1001-1096,1229-1346,1615-1690; N/decompress/huf_decompress.c:574-698).
@@ -24,9 +29,16 @@
 namespace zb {
 
 constexpr u32 FAST_MAXS = 43776;            // > 131072 / MINMATCH: more sequences cannot fit a 128 KB block
-constexpr u32 FAST_HUF_ENTRIES = 1u << HUF_TABLELOG_MAX;
-constexpr u32 FAST_FSE_ENTRIES = 512 + 256 + 512;  // LL | OF | ML, packed u32 entries nextState | nbBits << 16 | symbol << 24
+constexpr u32 FAST_HUF_LOG = 11;            // largest Huffman table the staged path takes (the reference never writes 2^12)
+constexpr u32 FAST_HUF_ENTRIES = 1u << FAST_HUF_LOG;
+constexpr u32 FAST_FSE_ENTRIES = 512 + 256 + 512;  // LL | OF | ML
 constexpr u32 FAST_FSE_OF = 512, FAST_FSE_ML = 768;
+constexpr u32 HUF_UNUSABLE = 0xFFFFFFFFu;
+
+// FSE cell of the staged path: extra bits of the code (bits 0..7) | nbBits (8..15) | new-state base (16..24) | code (25..30).
+// The byte-aligned bit counts make the sum of the three cells of a sequence carry both totals at once
+// (byte 0: offset + matchLength + litLength extra bits <= 63, byte 1: state bits <= 26).
+ZB_HD u32 fse2_pack(u32 e, u32 extra) { return extra | (((e >> 16) & 0xFF) << 8) | ((e & 0x1FF) << 16) | ((e >> 24) << 25); }
 
 struct DecDesc {
     u32 mode;            // 0 = not eligible (fused kernel handles the item), 1 = compressed block, 2 = raw block, 3 = rle block
@@ -35,11 +47,13 @@ struct DecDesc {
     u32 contentSize;
     u32 litMode, litSize, rawOff, rleByte, hufLog, nStreams;
     u32 sOff[4], sLen[4], oOff[4], oCnt[4];      // relative to the block content / the literal buffer
+    u32 sBits[4];                                // bits of Huffman stream k below its end mark (HUF_UNUSABLE: no end mark)
     u32 nbSeq, seqOff, seqLen;                   // sequence bitstream inside the block content
+    u32 seqBits;                                 // bits of the sequence stream below its end mark
     u32 logLL, logOF, logML;
     u32 regen;
-    u32 hufLitSize;      // litSize when the literals are Huffman coded, else 0 (sort key of the Huffman stage)
-    u32 pad[2];
+    u32 hufLitSize;      // litSize when the literals are Huffman coded, else 0 (sort key of the Huffman chains)
+    u32 seqUnusable;     // the sequence stream has no end mark: stC is final, nothing is decoded or executed
 };
 
 // ---------------------------------------------------------------------------------------- stage A
@@ -48,9 +62,9 @@ template <class C>
 ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize, size_t dstCapacity, DecDesc* d, u16* hufOut, u32* fseOut) {
     DecDesc L;   // built in registers/local, stored by lane 0 at the end
     L.mode = 0; L.stA1 = L.stB = L.stA2 = L.stC = L.stD = 0; L.regen = 0; L.nbSeq = 0; L.litMode = 0; L.litSize = 0; L.nStreams = 0;
-    L.blockOff = L.cSize = L.contentSize = L.rawOff = L.rleByte = L.hufLog = L.seqOff = L.seqLen = L.logLL = L.logOF = L.logML = 0;
-    for (int k = 0; k < 4; k++) { L.sOff[k] = L.sLen[k] = L.oOff[k] = L.oCnt[k] = 0; }
-    L.pad[0] = L.pad[1] = 0; L.hufLitSize = 0;
+    L.blockOff = L.cSize = L.contentSize = L.rawOff = L.rleByte = L.hufLog = L.seqOff = L.seqLen = L.seqBits = L.logLL = L.logOF = L.logML = 0;
+    for (int k = 0; k < 4; k++) { L.sOff[k] = L.sLen[k] = L.oOff[k] = L.oCnt[k] = L.sBits[k] = 0; }
+    L.seqUnusable = 0; L.hufLitSize = 0;
     do {
         if (srcSize < 9) break;
         if (load32(src) != MAGIC) break;
@@ -76,12 +90,21 @@ ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize,
         LitInfo li;
         size_t const lr = parse_literals(w, S, blk, cSize, fh.blockSizeMax, dstCapacity, &li);
         if (isErr(lr)) { L.stA1 = (u32)(0 - lr); break; }
+        if (li.mode == 2 && S.hufLog > FAST_HUF_LOG) { L.mode = 0; break; }     // legal, never written by the reference: fused kernel
         L.litMode = li.mode; L.litSize = li.litSize; L.rawOff = li.rawOff; L.rleByte = li.rleByte; L.nStreams = li.nStreams; L.hufLog = S.hufLog;
         for (int k = 0; k < 4; k++) { L.sOff[k] = li.sOff[k]; L.sLen[k] = li.sLen[k]; L.oOff[k] = li.oOff[k]; L.oCnt[k] = li.oCnt[k]; }
         if (li.mode == 2) {
             L.hufLitSize = li.litSize;
             u32 const nE = 1u << S.hufLog;
             for (u32 i = (u32)w.lane; i < nE; i += C::W) hufOut[i] = S.huf[i];
+            // a stream needs at least its end mark (HUF_decompress1X1 / BIT_initDStream: srcSize < 1 or a zero last byte is corruption)
+            for (u32 k = 0; k < li.nStreams; k++) {
+                L.sBits[k] = HUF_UNUSABLE;
+                if (li.sLen[k] < 1) { L.stB = E_corruption_detected; continue; }
+                u32 const last = blk[li.sOff[k] + li.sLen[k] - 1];
+                if (last == 0) { L.stB = E_corruption_detected; continue; }
+                L.sBits[k] = (li.sLen[k] - 1) * 8 + highbit32(last);
+            }
         }
         int nbSeq = 0;
         size_t const hr = parse_seq_section(w, S, blk + lr, cSize - lr, dstCapacity, &nbSeq);
@@ -93,13 +116,18 @@ ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize,
             for (int t = 0; t < 3; t++) {
                 u32 const nE = 1u << S.fseLog[t];
                 u32* const out = fseOut + (t == 0 ? 0 : t == 1 ? FAST_FSE_OF : FAST_FSE_ML);
-                // bits 10..14 of the copy carry the code's extra-bit count, so that stage C learns every bit count of
-                // a sequence from the three state entries alone
                 for (u32 i = (u32)w.lane; i < nE; i += C::W) {
                     u32 const e = S.fse[t][i], sym = e >> 24;
                     u32 const extra = t == 0 ? ZB_T.LL_bits[sym] : t == 1 ? sym : ZB_T.ML_bits[sym];
-                    out[i] = e | (extra << 10);
+                    out[i] = fse2_pack(e, extra);
                 }
+            }
+            // ZSTD_decompressSequences: BIT_initDStream fails on an empty stream or a zero last byte -> corruption_detected
+            if (L.seqLen < 1) { L.stC = E_corruption_detected; L.seqUnusable = 1; }
+            else {
+                u32 const last = blk[L.seqOff + L.seqLen - 1];
+                if (last == 0) { L.stC = E_corruption_detected; L.seqUnusable = 1; }
+                else L.seqBits = (L.seqLen - 1) * 8 + highbit32(last);
             }
         }
     } while (0);
@@ -108,169 +136,337 @@ ZB_HDN void dec_prepare(const C& w, DecShared& S, const u8* src, size_t srcSize,
     w.sync();
 }
 
-// ---------------------------------------------------------------------------------------- stage B
-// one thread per (frame, stream)
-ZB_HDN void dec_huf(DecDesc* d, int k, const u8* blk, const u16* huf, u8* lit) {
-    if (d->mode != 1 || d->stA1 || d->litMode != 2 || k >= (int)d->nStreams) return;
-    if (!huf_decode_stream(huf, d->hufLog, blk + d->sOff[k], d->sLen[k], lit + d->oOff[k], d->oCnt[k])) d->stB = E_corruption_detected;
+// ---------------------------------------------------------------------------------------- word sources
+// A backward bitstream is addressed in 32-bit words counted from the 16-byte aligned address at or below its first
+// byte: word k holds stream bits [32 k, 32 k + 32) of that numbering, the stream's own bits start at bit `floorBit`
+// (= 8 x the distance of the first byte from the aligned address).  Words below the first byte read as zero, the
+// word holding it is masked -- mirroring the reference's zero-filled container once a backward stream is exhausted
+// (N/common/bitstream.h:344-351).
+ZB_HD u32 shr_clamp(u32 v, u32 s) {      // v >> s for s in 0..32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(v, 0u, s);
+#else
+    return s >= 32 ? 0u : v >> s;
+#endif
 }
-
-// ---------------------------------------------------------------------------------------- stage C
-// one thread per frame: ZSTD_decodeSequence :1229-1346 for every sequence, offsets resolved against the
-// repcode history {1,4,8}; sequences are stored as litLength | matchLength << 18 | offset << 36 (each < 2^18
-// for a block of at most 128 KB; larger values can only come from corrupt input and are clamped to 2^18-1 /
-// 2^28-1, which the executor rejects exactly like the originals).
-// `fse` = the frame's three tables (FAST_FSE_ENTRIES u32, in shared memory on the GPU), `ct` = code tables
-// (shared memory copy on the GPU: per-lane indices would serialise in the constant cache).
-// The decoder is a small state machine (begin / step / end) so that a kernel can keep every lane of a warp busy:
-// a lane that finishes its frame picks up the next one while the other lanes keep stepping in lockstep.
-struct SeqDecoder {
-    DecDesc* d; const u32* tLL; const u32* tOF; const u32* tML; const CodeTables* ct; u64* seqOut;
-    BackBits B; u32 sLL, sOF, sML, rep0, rep1, rep2, k, nbSeq;
-
-    // false: nothing to decode for this item (not eligible, earlier error, no sequences, unusable stream)
-    ZB_HD bool begin(DecDesc* d_, const u8* blk, const u32* fse, const CodeTables* ct_, u64* out) {
-        d = d_;
-        if (d->mode != 1 || d->stA1 || d->stA2 || d->nbSeq == 0) return false;
-        const u8* const ip = blk + d->seqOff; size_t const left = d->seqLen;
-        if (left < 1 || ip[left - 1] == 0) { d->stC = E_corruption_detected; return false; }
-        tLL = fse; tOF = fse + FAST_FSE_OF; tML = fse + FAST_FSE_ML; ct = ct_; seqOut = out;
-        B.init(ip, (int)(left - 1) * 8 + (int)highbit32(ip[left - 1]));
-        rep0 = 1; rep1 = 4; rep2 = 8;
-        sLL = B.take(d->logLL); sOF = B.take(d->logOF); sML = B.take(d->logML);
-        k = 0; nbSeq = d->nbSeq;
-        return true;
+struct StreamGeom {
+    const u32* W;        // aligned base
+    int kFirst;          // word holding the first stream byte
+    u32 firstMask;       // valid bits of that word
+    u32 floorBit;        // bit index of the stream's first bit
+    ZB_HD void set(const u8* ip) {
+        uintptr_t const a = reinterpret_cast<uintptr_t>(ip);
+        W = reinterpret_cast<const u32*>(a & ~(uintptr_t)15);
+        u32 const sb = (u32)(a & 15);
+        kFirst = (int)(sb >> 2); firstMask = 0xFFFFFFFFu << (8 * (sb & 3)); floorBit = 8 * sb;
     }
-    // one sequence; true while more remain
-    ZB_HD bool step() {
-        // entry: nextState (bits 0..9) | extra bits of the code (10..14) | nbBits (16..23) | code (24..31)
-        u32 const eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
-        u32 const llc = eLL >> 24, ofc = eOF >> 24, mlc = eML >> 24;
-        u32 const llBits = (eLL >> 10) & 31, mlBits = (eML >> 10) & 31, ofBits = ofc;
-        u32 const nLL = (eLL >> 16) & 0xFF, nML = (eML >> 16) & 0xFF, nOF = (eOF >> 16) & 0xFF;
-        bool const lastSeq = (k + 1 == nbSeq);
-        // read order: offset bits, ML extra, LL extra, then LL / ML / OF state bits (ZSTD_decodeSequence :1229-1346)
-        u32 const ofVal = B.take(ofBits);
-        u32 const x = B.take(mlBits + llBits);
-        u32 const y = lastSeq ? 0 : B.take(nLL + nML + nOF);
-        u32 const matchLength = ct->ML_base[mlc] + (x >> llBits);
-        u32 const litLength = ct->LL_base[llc] + (x & ((1u << llBits) - 1));
-        u32 offset;
-        if (ofBits > 1) { offset = ((1u << ofBits) - 3) + ofVal; rep2 = rep1; rep1 = rep0; rep0 = offset; }
-        else {
-            u32 const ll0 = (llc == 0);          // :1300 tests litLength base == 0, true for code 0 only
-            if (ofBits == 0) { offset = ll0 ? rep1 : rep0; rep1 = ll0 ? rep0 : rep1; rep0 = offset; }
-            else {
-                u32 const idx = 1 + ll0 + ofVal;
-                u32 temp = (idx == 3) ? rep0 - 1 : (idx == 1 ? rep1 : rep2);
-                temp -= !temp;
-                if (idx != 1) rep2 = rep1;
-                rep1 = rep0; rep0 = temp; offset = temp;
-            }
-        }
-        if (!lastSeq) {
-            sLL = (eLL & 0x3FF) + (y >> (nML + nOF));
-            sML = (eML & 0x3FF) + ((y >> nOF) & ((1u << nML) - 1));
-            sOF = (eOF & 0x3FF) + (y & ((1u << nOF) - 1));
-        }
-        u64 const l = litLength > 0x3FFFF ? 0x3FFFF : litLength, m = matchLength > 0x3FFFF ? 0x3FFFF : matchLength;
-        u64 const o = offset > 0xFFFFFFFu ? 0xFFFFFFFu : offset;
-        seqOut[k] = l | (m << 18) | (o << 36);
-        return ++k < nbSeq;
-    }
-    ZB_HD void end() { if (B.pos != 0) d->stC = E_corruption_detected; }
+    ZB_HD u32 fix(int k, u32 raw) const { return k > kFirst ? raw : (k == kFirst ? raw & firstMask : 0u); }
+};
+// host / reference word source: straight from memory
+struct MemWords {
+    StreamGeom g;
+    ZB_HD u32 word(int k) const { return k < g.kFirst ? 0u : g.fix(k, g.W[k]); }
+    ZB_HD void fetch4(int k, u32& a, u32& b, u32& c, u32& d) const { a = word(k); b = word(k - 1); c = word(k - 2); d = word(k - 3); }
+    ZB_HD void advance(int) {}
 };
 
+// ---------------------------------------------------------------------------------------- stage C
+// One thread per frame: ZSTD_decodeSequence :1229-1346 for every sequence, offsets resolved against the repcode
+// history {1,4,8}; sequences are stored as litLength | matchLength << 18 | offset << 36 (each < 2^18 for a block of
+// at most 128 KB; larger values can only come from corrupt input and are clamped to 2^18-1 / 2^28-1, which the
+// executor rejects exactly like the originals).
+// One step = one sequence, branch free: the next 96 bits of the stream are assembled from four words, the three
+// cells give every bit count, and the three fields of the sequence (offset bits | length bits | state bits) are cut
+// out of that window.  A sequence reads at most 31 + 32 + 26 = 89 bits.
+struct SeqChain {
+    u32 sLL, sOF, sML, rep0, rep1, rep2;
+    int top;             // bit index of the next unread bit (drops below floorBit on overrun, then reads zeros)
+    u32 k, nbSeq;
+    u64* out;
+
+    template <class WS>
+    ZB_HD void begin(WS& ws, u32 floorBit, u32 seqBits, u32 logLL, u32 logOF, u32 logML, u32 nbSeq_, u64* out_) {
+        top = (int)(floorBit + seqBits) - 1;
+        rep0 = 1; rep1 = 4; rep2 = 8; k = 0; nbSeq = nbSeq_; out = out_;
+        u32 W0, W1, W2, W3; ws.fetch4(top >> 5, W0, W1, W2, W3);
+        u32 const c = 31u - ((u32)top & 31u);
+        u32 const V0 = fshl32(W1, W0, c);
+        u32 const t = logLL + logOF + logML;                 // <= 26
+        u32 const y = shr_clamp(V0, 32 - t);
+        sLL = y >> (logOF + logML); sOF = (y >> logML) & ((1u << logOF) - 1); sML = y & ((1u << logML) - 1);
+        top -= (int)t;
+        ws.advance(top >> 5);
+    }
+    // one sequence; `tLL/tOF/tML` = the frame's three tables (fse2 cells), `ct` = code tables
+    template <class WS>
+    ZB_HD void step(WS& ws, const u32* tLL, const u32* tOF, const u32* tML, const CodeTables* ct) {
+        u32 W0, W1, W2, W3; ws.fetch4(top >> 5, W0, W1, W2, W3);
+        u32 const c = 31u - ((u32)top & 31u);
+        u32 const V0 = fshl32(W1, W0, c), V1 = fshl32(W2, W1, c), V2 = fshl32(W3, W2, c);
+        u32 const eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
+        u32 const S = eLL + eOF + eML;
+        u32 const ofBits = eOF & 0xFF, llBits = eLL & 0xFF;
+        u32 const q2 = S & 0xFF, E = q2 - ofBits, nTot = (S >> 8) & 0xFF;
+        u32 const nOF = (eOF >> 8) & 0xFF, nML = (eML >> 8) & 0xFF;
+        // read order: offset bits, ML extra, LL extra, then LL / ML / OF state bits (ZSTD_decodeSequence :1229-1346)
+        u32 const ofVal = shr_clamp(V0, 32 - ofBits);
+        u32 const x = shr_clamp(fshl32(V1, V0, ofBits), 32 - E);
+        bool const far = q2 >= 32;
+        u32 const y = shr_clamp(fshl32(far ? V2 : V1, far ? V1 : V0, q2 & 31), 32 - nTot);
+        bool const lastSeq = (k + 1 == nbSeq);
+        top -= (int)(q2 + (lastSeq ? 0u : nTot));
+        ws.advance(top >> 5);                // the next step's four words are requested / waited for while this one finishes
+        u32 const llc = eLL >> 25, mlc = eML >> 25;
+        u32 const litLength = ct->LL_base[llc] + (x & ((1u << llBits) - 1));
+        u32 const matchLength = ct->ML_base[mlc] + (x >> llBits);
+        // offset / repcode history, all cases as selects: idx 0..3 = repcode slots (3: rep0 - 1), 4 = a new offset
+        u32 const ll0 = (llc == 0);          // :1300 tests litLength base == 0, true for code 0 only
+        u32 const idx = ofBits > 1 ? 4u : ofBits + ll0 + ofVal;
+        u32 cand = idx == 0 ? rep0 : idx == 1 ? rep1 : idx == 2 ? rep2 : idx == 3 ? rep0 - 1 : ((1u << ofBits) - 3) + ofVal;
+        cand -= !cand;                       // only a repcode can be zero here (rep0 - 1, or a corrupted history)
+        rep2 = idx >= 2 ? rep1 : rep2; rep1 = idx >= 1 ? rep0 : rep1; rep0 = cand;
+        sLL = ((eLL >> 16) & 0x1FF) + (y >> (nML + nOF));
+        sML = ((eML >> 16) & 0x1FF) + ((y >> nOF) & ((1u << nML) - 1));
+        sOF = ((eOF >> 16) & 0x1FF) + (y & ((1u << nOF) - 1));
+        u64 const l = umin(litLength, 0x3FFFFu), m = umin(matchLength, 0x3FFFFu), o = umin(cand, 0xFFFFFFFu);
+        out[k] = l | (m << 18) | (o << 36);
+        ++k;
+    }
+    ZB_HD bool more() const { return k < nbSeq; }
+    ZB_HD bool clean(u32 floorBit) const { return top + 1 == (int)floorBit; }       // every bit consumed, none borrowed
+};
+
+// host / emulator form of stage C for one frame
 ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables* ct, u64* seqOut) {
-    SeqDecoder D;
-    if (!D.begin(d, blk, fse, ct, seqOut)) return;
-    while (D.step()) {}
-    D.end();
+    if (d->mode != 1 || d->stA1 || d->stA2 || d->nbSeq == 0 || d->seqUnusable) return;
+    MemWords ws; ws.g.set(blk + d->seqOff);
+    SeqChain D;
+    D.begin(ws, ws.g.floorBit, d->seqBits, d->logLL, d->logOF, d->logML, d->nbSeq, seqOut);
+    while (D.more()) D.step(ws, fse, fse + FAST_FSE_OF, fse + FAST_FSE_ML, ct);
+    if (!D.clean(ws.g.floorBit)) d->stC = E_corruption_detected;
+}
+
+// ---------------------------------------------------------------------------------------- stage B
+// One thread per Huffman stream (HUF_decompress1X1_usingDTable_internal_body :574-595): the unread bits sit left
+// aligned in a 64-bit register pair, the table index is a shift of its upper half, a 32-bit word slides in whenever 32
+// bits or fewer are left.  step4() = four symbols and one aligned 32-bit store; step1() = one symbol (head / tail).
+struct HufChain {
+    u32 hi, lo;          // window, first unread bit on top of hi
+    int avail;           // valid bits in the window
+    int kNext;           // word that slides in next
+    int budget;          // stream bits not yet moved into the window or consumed: ends at 0 exactly
+    u32 left;            // symbols to go
+    u8* op;
+
+    template <class WS>
+    ZB_HD void begin(WS& ws, u32 floorBit, u32 bits, u8* dst, u32 n) {
+        int const top = (int)(floorBit + bits) - 1;
+        int const k0 = top >> 5;
+        u32 const c = 31u - ((u32)top & 31u);            // bits of word k0 above the end mark
+        u32 const W0 = ws.word(k0), W1 = ws.word(k0 - 1);
+        hi = fshl32(W1, W0, c); lo = W1 << c;            // whole words only: the low c bits stay empty until the next refill
+        avail = 64 - (int)c; kNext = k0 - 2;
+        budget = (int)bits;                              // consumed bits are counted against this
+        left = n; op = dst;
+    }
+    template <class WS>
+    ZB_HD void refill(WS& ws) {
+        if (avail <= 32) {                               // 9 <= avail here: at most 2 x 12 bits leave between two refills
+            u32 const wv = ws.word(kNext); kNext--;
+            hi |= shr_clamp(wv, (u32)avail);             // avail == 32: nothing reaches hi
+            lo = wv << (32u - (u32)avail);
+            avail += 32;
+            ws.advance(kNext);
+        }
+    }
+    ZB_HD u32 symbol(const u16* table, u32 sh) {
+        u32 const e = table[hi >> sh];
+        u32 const nb = e >> 8;
+        hi = fshl32(lo, hi, nb); lo <<= nb;              // nb <= 12
+        avail -= (int)nb; budget -= (int)nb;
+        return e & 0xFF;
+    }
+    template <class WS>
+    ZB_HD void step4(WS& ws, const u16* table, u32 sh) {
+        refill(ws); u32 const s0 = symbol(table, sh), s1 = symbol(table, sh);     // avail > 32 >= 2 x 12 bits
+        refill(ws); u32 const s2 = symbol(table, sh), s3 = symbol(table, sh);
+        *reinterpret_cast<u32*>(op) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+        op += 4; left -= 4;
+    }
+    template <class WS>
+    ZB_HD void step1(WS& ws, const u16* table, u32 sh) {
+        refill(ws); *op++ = (u8)symbol(table, sh); left--;
+    }
+    ZB_HD bool aligned4() const { return (reinterpret_cast<uintptr_t>(op) & 3) == 0; }
+    ZB_HD bool clean() const { return budget == 0; }
+};
+
+// host / emulator form of stage B: stream k of one frame
+ZB_HDN void dec_huf(DecDesc* d, int k, const u8* blk, const u16* huf, u8* lit) {
+    if (d->mode != 1 || d->stA1 || d->litMode != 2 || k >= (int)d->nStreams || d->sBits[k] == HUF_UNUSABLE) return;
+    MemWords ws; ws.g.set(blk + d->sOff[k]);
+    HufChain H;
+    H.begin(ws, ws.g.floorBit, d->sBits[k], lit + d->oOff[k], d->oCnt[k]);
+    u32 const sh = 32 - d->hufLog;
+    while (H.left) { if (H.left >= 4 && H.aligned4()) H.step4(ws, huf, sh); else H.step1(ws, huf, sh); }
+    if (!H.clean()) d->stB = E_corruption_detected;
 }
 
 // ---------------------------------------------------------------------------------------- stage D
-// warp per frame.  Returns the item's final result (regenerated size or error code, libzstd convention).
+// Warp per frame, "byte gather" (ZSTD_execSequence :1001-1096 without its ordering): groups of EXEC_G sequences get
+// their output / literal positions by prefix sums and go to shared memory as 16-byte records; then the group's
+// output span is produced 128 bytes per round, four consecutive bytes per lane.  A byte finds the sequence it
+// belongs to through a small map of the sequence starts inside the round, and its source: a literal, or the byte
+// `offset` back -- folded into the match's own history when the match overlaps itself (offset < position in
+// match), and chased through the map while it still points into the round being written.  Everything before the
+// round is final, so no lane ever waits for another.
+constexpr u32 EXEC_SPL = 4;                  // sequences per lane and group
+constexpr u32 EXEC_G = 32 * EXEC_SPL;      // on a 32-lane warp
+struct alignas(16) ExecRec { u32 o, md, ls, off; };      // output start, match start, literal start, offset
+struct ExecShared {
+    ExecRec rec[EXEC_G + 1];
+    u32 map[32];         // round: byte j -> 1 + index (relative to the round's first sequence) of the sequence starting there
+    u32 own[32];         // round: byte j -> that index, after the fill
+};
+
+ZB_HD u32 exec_mod(u32 a, u32 b) { return a % b; }
+
 template <class C>
-ZB_HDN size_t dec_exec(const C& w, const DecDesc* dp, const u8* item, const u8* litBuf, const u64* seqs, u8* dst, size_t cap) {
+ZB_HDN size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* item, const u8* litBuf, const u64* seqs, u8* dst, size_t cap) {
     DecDesc const& d = *dp;
-    if (d.mode == 2) {           // raw block
-        if (d.cSize > cap) return ERR(E_dstSize_tooSmall);
+    if (d.mode == 2 || d.mode == 3) {            // raw / rle block: 16-byte stores once dst is aligned
+        u32 const n = d.mode == 2 ? d.cSize : d.regen;
+        if (n > cap) return ERR(E_dstSize_tooSmall);
         const u8* const s = item + d.blockOff;
-        for (u32 j = (u32)w.lane; j < d.cSize; j += C::W) dst[j] = s[j];
+        u32 const v1 = d.rleByte * 0x01010101u;
+        u32 head = (u32)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15); if (head > n) head = n;
+        for (u32 j = (u32)w.lane; j < head; j += C::W) dst[j] = d.mode == 2 ? s[j] : (u8)d.rleByte;
+        u32 const body = (n - head) / 16;
+        for (u32 j = (u32)w.lane; j < body; j += C::W) {
+            u32 a0 = v1, a1 = v1, a2 = v1, a3 = v1;
+            if (d.mode == 2) { u64 const lo = load64(s + head + 16 * j), hi = load64(s + head + 16 * j + 8); a0 = (u32)lo; a1 = (u32)(lo >> 32); a2 = (u32)hi; a3 = (u32)(hi >> 32); }
+            u32* const t = reinterpret_cast<u32*>(dst + head + 16 * j);
+#if defined(__CUDA_ARCH__)
+            *reinterpret_cast<uint4*>(t) = make_uint4(a0, a1, a2, a3);
+#else
+            t[0] = a0; t[1] = a1; t[2] = a2; t[3] = a3;
+#endif
+        }
+        for (u32 j = head + body * 16 + (u32)w.lane; j < n; j += C::W) dst[j] = d.mode == 2 ? s[j] : (u8)d.rleByte;
         w.sync();
-        return d.cSize == d.contentSize ? d.cSize : ERR(E_corruption_detected);
-    }
-    if (d.mode == 3) {           // rle block
-        if (d.regen > cap) return ERR(E_dstSize_tooSmall);
-        u8 const v = (u8)d.rleByte;
-        for (u32 j = (u32)w.lane; j < d.regen; j += C::W) dst[j] = v;
-        w.sync();
-        return d.regen == d.contentSize ? d.regen : ERR(E_corruption_detected);
+        return n == d.contentSize ? n : ERR(E_corruption_detected);
     }
     // error precedence of the fused decoder: literals header/table, Huffman streams, sequences header/tables, then execution
     if (d.stA1) return ERR((int)d.stA1);
     if (d.stB) return ERR((int)d.stB);
     if (d.stA2) return ERR((int)d.stA2);
     if (d.nbSeq && cap == 0) return ERR(E_dstSize_tooSmall);
-    if (d.nbSeq && d.stC && d.seqLen < 1) return ERR((int)d.stC);            // unusable stream: nothing was decoded
-    if (d.nbSeq && d.stC && (item + d.blockOff + d.seqOff)[d.seqLen - 1] == 0) return ERR((int)d.stC);
+    if (d.nbSeq && d.seqUnusable) return ERR((int)d.stC);            // unusable stream: nothing was decoded
     const u8* const lit = d.litMode == 0 ? item + d.blockOff + d.rawOff : litBuf;
-    bool const rle = d.litMode == 1; u8 const rleByte = (u8)d.rleByte;
+    bool const rle = d.litMode == 1; u32 const rleByte = d.rleByte;
     u32 const litSize = d.litSize, nbSeq = d.nbSeq;
+    u32 const A = (u32)(reinterpret_cast<uintptr_t>(dst) & 3);      // rounds are aligned to 128 bytes of (dst - A)
+    u8* const dstA = dst - A;
+    constexpr u32 G = (u32)C::W * EXEC_SPL, ROUND = 4u * (u32)C::W;     // 128 sequences per group, 128 bytes per round on a 32-lane warp
     u32 op = 0, lp = 0;     // output / literal cursors (uniform)
-    for (u32 base = 0; base < nbSeq; base += C::W) {
-        u32 const i = base + (u32)w.lane;
-        u64 const q = i < nbSeq ? seqs[i] : 0;
-        u32 const ll = (u32)(q & 0x3FFFF), ml = (u32)((q >> 18) & 0x3FFFF), off = (u32)(q >> 36);
-        u32 const preOut = w.exscan(ll + ml), preLit = w.exscan(ll);
-        u32 const o = op + preOut, ls = lp + preLit, md = o + ll;
-        // validity in sequence order (ZSTD_execSequenceEnd :919-932)
-        u32 code = 0;
-        if (i < nbSeq) {
-            if ((size_t)ll + ml > cap - (size_t)(o < cap ? o : cap) || o > cap) code = E_dstSize_tooSmall;
-            else if (ll > litSize - (ls < litSize ? ls : litSize) || ls > litSize) code = E_corruption_detected;
-            else if (off > md) code = E_corruption_detected;
+    for (u32 base = 0; base < nbSeq; base += G) {
+        // ---- the group's sequences: lane owns EXEC_SPL consecutive ones
+        u32 ll[EXEC_SPL], ml[EXEC_SPL], off[EXEC_SPL];
+        u32 sumO = 0, sumL = 0;
+        for (u32 t = 0; t < EXEC_SPL; t++) {
+            u32 const i = base + (u32)w.lane * EXEC_SPL + t;
+            u64 const q = i < nbSeq ? seqs[i] : 0;
+            ll[t] = (u32)(q & 0x3FFFF); ml[t] = (u32)((q >> 18) & 0x3FFFF); off[t] = (u32)(q >> 36);
+            sumO += ll[t] + ml[t]; sumL += ll[t];
+        }
+        u32 o = op + w.exscan(sumO), ls = lp + w.exscan(sumL);
+        // validity in sequence order (ZSTD_execSequenceEnd :919-932); `bad` = first failing sequence of the lane
+        u32 code = 0, badAt = G;
+        for (u32 t = 0; t < EXEC_SPL; t++) {
+            u32 const i = base + (u32)w.lane * EXEC_SPL + t;
+            u32 const md = o + ll[t];
+            if (i < nbSeq && !code) {
+                if ((size_t)ll[t] + ml[t] > cap - (size_t)(o < cap ? o : cap) || o > cap) code = E_dstSize_tooSmall;
+                else if (ll[t] > litSize - (ls < litSize ? ls : litSize) || ls > litSize) code = E_corruption_detected;
+                else if (off[t] > md) code = E_corruption_detected;
+                if (code) badAt = (u32)w.lane * EXEC_SPL + t;
+            }
+            ExecRec r; r.o = o; r.md = md; r.ls = ls; r.off = off[t];
+            X.rec[(u32)w.lane * EXEC_SPL + t] = r;
+            o = md + ml[t]; ls += ll[t];
         }
         u32 const badMask = w.ballot(code != 0);
-        u32 const good = badMask ? ((1u << ctz32(badMask)) - 1) : C::FULL;      // lanes before the first failure
-        bool const mine = ((good >> w.lane) & 1) && i < nbSeq;
-        // literals: short runs by their own lane, long ones by everybody
-        if (mine && ll && ll <= 32) { if (rle) { for (u32 k = 0; k < ll; k++) dst[o + k] = rleByte; } else copy_fwd(dst + o, lit + ls, ll); }
-        {   u32 big = w.ballot(mine && ll > 32);
-            while (big) {
-                int const b = (int)ctz32(big); big &= big - 1;
-                u32 const L = w.shfl(ll, b), oo = w.shfl(o, b), lss = w.shfl(ls, b);
-                for (u32 k = (u32)w.lane; k < L; k += C::W) dst[oo + k] = rle ? rleByte : lit[lss + k];
-            } }
+        u32 nGood = nbSeq - base < G ? nbSeq - base : G;          // sequences of the group to execute
+        u32 failCode = 0;
+        if (badMask) { int const fl = (int)ctz32(badMask); nGood = w.shfl(badAt, fl); failCode = w.shfl(code, fl); }
+        // end of the good prefix: start of sequence nGood (a sentinel record closes the table)
+        u32 const endO = w.shfl(o, C::W - 1), endL = w.shfl(ls, C::W - 1);
+        if (w.lane == 0 && nGood == G) { ExecRec r; r.o = endO; r.md = endO; r.ls = endL; r.off = 0; X.rec[G] = r; }
         w.sync();
-        // matches: everything before the first unfinished match destination is final; a match whose source ends
-        // there may run now, in its own lane (byte-serial, so overlapping copies replicate correctly)
-        u32 pending = w.ballot(mine && ml > 0);
-        while (pending) {
-            int const f = (int)ctz32(pending);
-            u32 const frontier = w.shfl(md, f), fml = w.shfl(ml, f);
-            if (fml > 64) {          // long match at the frontier: all lanes, period trick for overlaps
-                u32 const foff = w.shfl(off, f);
-                u8* const t = dst + frontier; const u8* const m = t - foff;
-                if (foff >= fml) { for (u32 k = (u32)w.lane; k < fml; k += C::W) t[k] = m[k]; }
-                else if (C::W == 1) { for (u32 k = 0; k < fml; k++) t[k] = m[k]; }
-                else { for (u32 k = (u32)w.lane; k < fml; k += C::W) t[k] = m[k % foff]; }
-                pending &= pending - 1;
-                w.sync();
-                continue;
+        u32 const gEnd = X.rec[nGood].o;          // for nGood < G that is a real record's start
+        u32 const gEndL = X.rec[nGood].ls;
+        // ---- rounds over [op, gEnd)
+        u32 cur = 0;                              // first sequence that is not entirely before the round
+        for (u32 rb = (op + A) & ~(ROUND - 1); rb < gEnd + A; rb += ROUND) {          // rb: round start in (dst - A) coordinates
+            u32 const p0 = rb > A ? rb - A : 0;                               // first output position of the round (may precede op)
+            // map of sequence starts inside the round
+            X.map[w.lane] = 0;
+            w.sync();
+            for (u32 t = 0; t < 2; t++) {          // a round holds at most ROUND / 3 + 1 starts (43 of 64 candidates on a warp)
+                u32 const j = cur + (u32)w.lane + (u32)C::W * t;
+                if (j < nGood) { u32 const so = X.rec[j].o + A; if (so >= rb && so < rb + ROUND) reinterpret_cast<u8*>(X.map)[so - rb] = (u8)(j - cur + 1); }
             }
-            bool const ready = ((pending >> w.lane) & 1) && ((int)w.lane == f || (ml <= 64 && md - off + ml <= frontier));
-            if (ready) copy_fwd(dst + md, dst + md - off, ml);
-            pending &= ~w.ballot(ready);
+            w.sync();
+            u32 const mw = X.map[w.lane];
+            // running maximum over the round = index of the sequence each byte belongs to
+            u32 b0 = mw & 0xFF, b1 = (mw >> 8) & 0xFF, b2 = (mw >> 16) & 0xFF, b3 = mw >> 24;
+            b1 = umax(b0, b1); b2 = umax(b1, b2); b3 = umax(b2, b3);
+            u32 run = b3;
+            for (int s = 1; s < C::W; s <<= 1) { u32 const t = w.shfl(run, (w.lane - s) & (C::W - 1)); if (w.lane >= s) run = umax(run, t); }
+            u32 const before = w.shfl(run, (w.lane - 1) & (C::W - 1));
+            u32 const e = w.lane ? before : 0;
+            b0 = umax(b0, e); b1 = umax(b1, e); b2 = umax(b2, e); b3 = umax(b3, e);
+            // value v > 0: sequence cur + v - 1; 0: the sequence that began before the round (cur)
+            u32 const u0 = b0 ? b0 - 1 : 0, u1 = b1 ? b1 - 1 : 0, u2 = b2 ? b2 - 1 : 0, u3 = b3 ? b3 - 1 : 0;
+            X.own[w.lane] = u0 | (u1 << 8) | (u2 << 16) | (u3 << 24);
+            w.sync();
+            u32 val = 0, validMask = 0;
+            for (u32 t = 0; t < 4; t++) {
+                u32 const v = rb + 4 * (u32)w.lane + t;            // (dst - A) coordinate
+                if (v < op + A || v >= gEnd + A) continue;
+                u32 p = v - A;
+                u32 const u = t == 0 ? u0 : t == 1 ? u1 : t == 2 ? u2 : u3;
+                ExecRec r = X.rec[cur + u];
+                u32 byte;
+                for (;;) {
+                    if (p < r.md) { byte = rle ? rleByte : lit[r.ls + (p - r.o)]; break; }
+                    u32 const k = p - r.md;
+                    u32 const src = r.md - r.off + (k < r.off ? k : exec_mod(k, r.off));
+                    if (src < p0 || src < op) { byte = dst[src]; break; }             // final: written before this round / this group
+                    // the source is produced in this very round: look at what produces it
+                    p = src;
+                    r = X.rec[cur + reinterpret_cast<const u8*>(X.own)[src + A - rb]];
+                }
+                val |= byte << (8 * t); validMask |= 1u << t;
+            }
+            if (validMask == 15) *reinterpret_cast<u32*>(dstA + rb + 4 * (u32)w.lane) = val;
+            else for (u32 t = 0; t < 4; t++) if ((validMask >> t) & 1) dstA[rb + 4 * (u32)w.lane + t] = (u8)(val >> (8 * t));
+            // next round starts with the sequence holding this round's last byte (or the one after it, if it ends there)
+            u32 const lastU = w.shfl(u3, C::W - 1);
+            u32 nc = cur + lastU;
+            w.sync();
+            while (nc < nGood && X.rec[nc + 1].o + A <= rb + ROUND) nc++;     // rec[nGood] exists (sentinel or a real record)
+            cur = nc < nGood ? nc : (nGood ? nGood - 1 : 0);
             w.sync();
         }
-        if (badMask) return ERR((int)w.shfl(code, (int)ctz32(badMask)));
-        op += w.bcast(preOut + ll + ml, C::W - 1); lp += w.bcast(preLit + ll, C::W - 1);
+        if (failCode) return ERR((int)failCode);
+        op = gEnd; lp = gEndL;
+        w.sync();
     }
     if (nbSeq && d.stC) return ERR((int)d.stC);
     {   u32 const last = litSize - lp;
         if (last > cap - op) return ERR(E_dstSize_tooSmall);
-        for (u32 k = (u32)w.lane; k < last; k += C::W) dst[op + k] = rle ? rleByte : lit[lp + k];
+        for (u32 k = (u32)w.lane; k < last; k += C::W) dst[op + k] = rle ? (u8)rleByte : lit[lp + k];
         op += last;
         w.sync(); }
     return op == d.contentSize ? op : ERR(E_corruption_detected);
