@@ -187,6 +187,24 @@ ZSTDB200_API size_t zstdb200_compress_chunks(zstdb200_ctx* ctx, int level, const
  * size, e.g. from ZSTD_getFrameContentSize; out: regenerated size or error code). */
 ZSTDB200_API size_t zstdb200_decompress_frames(zstdb200_ctx* ctx, const void* src, const size_t* frameSizes, size_t nFrames,
                                                void* dst, size_t dstCapacity, size_t* dstSizes);
+/* Asynchronous forms of the two calls above: `_begin` queues the copy-in, the kernels and the copy-out of the sizes on work set
+ * `slot` (0 .. ZSTDB200_SLOTS-1) and returns; `_end` waits for them and (compression: copies the packed frames out, then)
+ * reports like the synchronous call.  Different slots overlap: with begin(0) begin(1) end(0) begin(0) end(1) ... the copy-in of
+ * batch k+1 and the copy-out of batch k-1 ride on the two copy engines while batch k is in the kernels, so a stream of batches
+ * costs max(kernels, copies) per batch instead of their sum.  This is what a JNI stream loop over direct buffers
+ * (N/jni_outputstream_zstd.c:59-123, N/jni_directbuffercompress_zstd.c) or bench.py's end-to-end leg drives.  Buffers must stay
+ * valid and untouched between begin and end; page-locked memory (cudaHostAlloc, or zstdb200_host_register on a direct
+ * buffer) makes the copies truly asynchronous.  One operation per slot at a time; a context is still single-threaded. */
+#define ZSTDB200_SLOTS 4
+ZSTDB200_API size_t zstdb200_compress_chunks_begin(zstdb200_ctx* ctx, int slot, int level, const void* src, size_t srcSize, size_t chunkSize);
+ZSTDB200_API size_t zstdb200_compress_chunks_end(zstdb200_ctx* ctx, int slot, void* dst, size_t dstCapacity, size_t* frameSizes, size_t* dstSize);
+ZSTDB200_API size_t zstdb200_decompress_frames_begin(zstdb200_ctx* ctx, int slot, const void* src, const size_t* frameSizes, size_t nFrames,
+                                                     void* dst, size_t dstCapacity, const size_t* dstSizes);
+ZSTDB200_API size_t zstdb200_decompress_frames_end(zstdb200_ctx* ctx, int slot, size_t* dstSizes);
+/* page-lock / release a caller-owned host range (a DirectByteBuffer's address range) so that the copies of the calls above run
+ * on the copy engines without a staging pass; returns 0 or an error code */
+ZSTDB200_API size_t zstdb200_host_register(void* ptr, size_t bytes);
+ZSTDB200_API size_t zstdb200_host_unregister(void* ptr);
 /* scattered host buffers (what a JNI batch entry point would pass after pinning n arrays) */
 ZSTDB200_API size_t zstdb200_compress_batch(zstdb200_ctx* ctx, int level, size_t n, const void* const* src, const size_t* srcSize,
                                             void* const* dst, const size_t* dstCapacity, size_t* dstSize);

@@ -51,3 +51,10 @@ for rep in range(reps):
     L.zstdb200_kernel_times(ctx.handle, buf, 4096)
     print(f"rep {rep}: {ms:.3f} ms -> {n*131072/ms/1e6:.1f} GB/s out | {buf.value.decode()}", flush=True)
 print("final roundtrip ok:", bool(torch.equal(d_back, d_src)))
+for roles in (1, 2):      # which chains bound k_dec_chains: sequence chains alone, Huffman chains alone (outputs are wrong here)
+    ctx.setOption("chain_roles", roles)
+    for rep in range(2):
+        decomp(); torch.cuda.synchronize()
+        L.zstdb200_kernel_times(ctx.handle, buf, 4096)
+    print(f"roles={roles}: {buf.value.decode()}", flush=True)
+ctx.setOption("chain_roles", 3)

@@ -20,6 +20,12 @@ for l in dis.split("\n"):
 cands = [k for k in funcs if kname in k and len(funcs[k]) > 50]
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(sass.split("\n")))
+# a report may hold several launches: one section per launch, each headed by a "Kernel Name" row; take the first that matches
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+pick = [i for i in starts if kname in rows[i][1]]
+if pick:
+    a = pick[0]; b = min([x for x in starts if x > a] + [len(rows)])
+    rows = rows[a:b]
 hdr = rows[1]; si = hdr.index("Warp Stall Sampling (All Samples)"); ii = hdr.index("Instructions Executed")
 ncu = [(re.sub(r"\s+", " ", r[1]).strip(), int(r[si] or 0), int(r[ii] or 0)) for r in rows[2:] if len(r) > ii and r[si].isdigit()]
 match = [k for k in cands if len(funcs[k]) == len(ncu)]

@@ -27,7 +27,7 @@ constexpr int CH_RING_DEPTH = 4;         // cells requested below the one being 
 constexpr u32 CH_FSE_SLOT = FAST_FSE_ENTRIES * 4, CH_HUF_SLOT = FAST_HUF_ENTRIES * 2;
 constexpr u32 CH_OFF_HUF = CH_FSE_WARPS * CH_FSE_LANES * CH_FSE_SLOT;
 constexpr u32 CH_OFF_RING = CH_OFF_HUF + CH_HUF_WARPS * 8 * CH_HUF_SLOT;
-constexpr u32 CH_OFF_CT = CH_OFF_RING + CH_WARPS * CH_RING_GROUPS * 512;
+constexpr u32 CH_OFF_CT = CH_OFF_RING + CH_WARPS * 32 * (16 + CH_RING_GROUPS * 16);
 constexpr u32 CH_OFF_BAR = CH_OFF_CT + ((sizeof(CodeTables) + 15) / 16) * 16;
 constexpr u32 CH_SMEM = CH_OFF_BAR + (CH_FSE_WARPS * CH_FSE_LANES + CH_HUF_WARPS * 8) * 8;
 
@@ -53,37 +53,64 @@ __device__ __forceinline__ bool mbar_wait(u32 bar, u32 parity) {
     return false;
 }
 
-// word source of a chain on the GPU: the lane's ring
+// word source of a chain on the GPU: the lane's ring.  32 words (8 groups of 16 bytes) plus a mirror cell below them that
+// repeats the top group, so that the four words k, k-1, k-2, k-3 of a window are always at one address and three immediate
+// offsets below it -- no wrap-around arithmetic on the chain.
+constexpr u32 CH_RING_LANE_BYTES = 16 + CH_RING_GROUPS * 16;       // mirror cell + ring
+constexpr u32 CH_RING_WARP_BYTES = 32 * CH_RING_LANE_BYTES;
 struct RingWords {
     StreamGeom g;
-    u32 cell0;           // shared-memory address of the lane's cell in ring slot 0
+    u32 ring0;           // shared-memory address of the lane's ring word 0 (the mirror cell sits 16 bytes below)
     int gIssued;         // lowest 16-byte group requested so far
-    __device__ __forceinline__ u32 raw(int k) const {
-        u32 v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(cell0 + (((u32)k >> 2) & (CH_RING_GROUPS - 1)) * 512u + ((u32)k & 3u) * 4u) : "memory");
-        return v;
-    }
+    __device__ __forceinline__ u32 lds(u32 addr) const { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+    __device__ __forceinline__ u32 raw(int k) const { return lds(ring0 + (((u32)k & (CH_RING_GROUPS * 4 - 1)) << 2)); }
     __device__ __forceinline__ u32 word(int k) const { return k < g.kFirst ? 0u : g.fix(k, raw(k)); }
     __device__ __forceinline__ void fetch4(int k, u32& a, u32& b, u32& c, u32& d) const {
-        if (k >= 8) { a = raw(k); b = raw(k - 1); c = raw(k - 2); d = raw(k - 3); }     // kFirst <= 3: no masks up here
-        else { a = word(k); b = word(k - 1); c = word(k - 2); d = word(k - 3); }
+        if (k >= 8) {                                    // kFirst <= 3: no masks up here
+            u32 const at = ring0 + (((u32)k & (CH_RING_GROUPS * 4 - 1)) << 2);
+            asm volatile("ld.shared.u32 %0, [%4];\n\tld.shared.u32 %1, [%4+-4];\n\tld.shared.u32 %2, [%4+-8];\n\tld.shared.u32 %3, [%4+-12];"
+                         : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(at) : "memory");
+        } else { a = word(k); b = word(k - 1); c = word(k - 2); d = word(k - 3); }
     }
-    // the reader now stands at word k: request the cells down to CH_RING_DEPTH groups below it, then make sure the
-    // group of k and the one below have landed (all but the CH_RING_DEPTH - 1 youngest requests)
-    __device__ __forceinline__ void advance(int k) {
-        int const want = (k >> 2) - CH_RING_DEPTH;
-        while (gIssued > want) {
-            gIssued--;
-            if (gIssued >= 0) cp_async16(cell0 + ((u32)gIssued & (CH_RING_GROUPS - 1)) * 512u, g.W + 4 * gIssued);
-            cp_async_commit();
+    __device__ __forceinline__ void fetch4_fast(int k, u32& a, u32& b, u32& c, u32& d) const {
+        u32 const at = ring0 + (((u32)k & (CH_RING_GROUPS * 4 - 1)) << 2);
+        asm volatile("ld.shared.u32 %0, [%4];\n\tld.shared.u32 %1, [%4+-4];\n\tld.shared.u32 %2, [%4+-8];\n\tld.shared.u32 %3, [%4+-12];"
+                     : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(at) : "memory");
+    }
+    // advance() without a branch: the copies are predicated, a (possibly empty) group is committed every time -- empty groups only
+    // make the real requests look older to wait_group, which keeps its guarantee
+    __device__ __forceinline__ void advance_fast(int k) {
+        bool const need = gIssued > (k >> 2) - CH_RING_DEPTH;
+        gIssued -= need ? 1 : 0;
+        u32 const m = (u32)gIssued & (CH_RING_GROUPS - 1);
+        u32 const p1 = (need && gIssued >= 0) ? 1u : 0u, p2 = (p1 && m == CH_RING_GROUPS - 1) ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tsetp.ne.u32 q, %4, 0;\n\t"
+                     "@p cp.async.cg.shared.global [%0], [%2], 16;\n\t@q cp.async.cg.shared.global [%1], [%2], 16;\n\t"
+                     "cp.async.commit_group;\n\t}"
+                     :: "r"(ring0 + m * 16), "r"(ring0 - 16), "l"(g.W + 4 * gIssued), "r"(p1), "r"(p2) : "memory");
+        cp_async_wait<CH_RING_DEPTH - 1>();
+    }
+    __device__ __forceinline__ void request_next() {    // one more group below the lowest requested one
+        gIssued--;
+        if (gIssued >= 0) {
+            u32 const m = (u32)gIssued & (CH_RING_GROUPS - 1);
+            cp_async16(ring0 + m * 16, g.W + 4 * gIssued);
+            if (m == CH_RING_GROUPS - 1) cp_async16(ring0 - 16, g.W + 4 * gIssued);      // the top group also fills the mirror cell
         }
+        cp_async_commit();
+    }
+    // the reader now stands at word k (at most one group below where it stood): keep CH_RING_DEPTH groups requested below
+    // it, then make sure the group of k and the one below have landed (all but the CH_RING_DEPTH - 1 youngest requests)
+    __device__ __forceinline__ void advance(int k) {
+        if (gIssued > (k >> 2) - CH_RING_DEPTH) request_next();
         cp_async_wait<CH_RING_DEPTH - 1>();
     }
     __device__ __forceinline__ void start(const u8* ip, u32 bits) {
         g.set(ip);
         int const k = ((int)(g.floorBit + bits) - 1) >> 5;
         gIssued = (k >> 2) + 1;
-        advance(k);
+        while (gIssued > (k >> 2) - CH_RING_DEPTH) request_next();
+        cp_async_wait<CH_RING_DEPTH - 1>();
     }
 };
 
@@ -91,6 +118,7 @@ struct ChainsArgs {
     const u8* srcBase; const u64* srcOff; u32 n; DecDesc* descs;
     const u32* fseBase; const u16* hufBase; u64* seqBase; u8* litBase; size_t litStride;
     u32* counterSeq; u32* counterHuf; const u32* orderSeq; const u32* orderHuf;
+    u32 roles;           // experiments: bit 0 = run the sequence chains, bit 1 = run the Huffman chains (3 = both, the product setting)
 };
 
 __device__ __forceinline__ void chains_fse_warp(const ChainsArgs& a, unsigned char* smem, int warp, int lane) {
@@ -102,11 +130,13 @@ __device__ __forceinline__ void chains_fse_warp(const ChainsArgs& a, unsigned ch
     const CodeTables* const ct = reinterpret_cast<const CodeTables*>(smem + CH_OFF_CT);
     u32 const bar = smem_u32(smem + CH_OFF_BAR + slot * 8);
     u32 parity = 0;
-    RingWords ws; ws.cell0 = smem_u32(smem + CH_OFF_RING + warp * (CH_RING_GROUPS * 512) + lane * 16); ws.gIssued = 0;
-    SeqChain D; D.k = D.nbSeq = 0;
+    RingWords ws; ws.ring0 = smem_u32(smem + CH_OFF_RING + warp * CH_RING_WARP_BYTES + lane * CH_RING_LANE_BYTES + 16); ws.gIssued = 0;
+    SeqChain D; D.k = D.nbSeq = 0; D.top = 0; D.sLL = D.sOF = D.sML = 0; D.rep0 = D.rep1 = D.rep2 = 1; D.out = nullptr;
     DecDesc* d = nullptr;
     bool live = false, exhausted = false;
     for (;;) {
+        // the common iteration: every lane in the middle of a frame -- one vote, then a straight line
+        if (!__any_sync(MASK, !live || !D.plain())) { D.step_fast(ws, tab, tab + FAST_FSE_OF, tab + FAST_FSE_ML, ct); continue; }
         if (!live && !exhausted) {
             u32 item = atomicAdd(a.counterSeq, 1u);
             if (item >= a.n) exhausted = true;
@@ -151,12 +181,13 @@ __device__ __forceinline__ void chains_huf_warp(const ChainsArgs& a, unsigned ch
     u32 const tabAddr = smem_u32(tab);
     u32 const bar = smem_u32(smem + CH_OFF_BAR + (CH_FSE_WARPS * CH_FSE_LANES + slot) * 8);
     u32 parity = 0;
-    RingWords ws; ws.cell0 = smem_u32(smem + CH_OFF_RING + warp * (CH_RING_GROUPS * 512) + lane * 16); ws.gIssued = 0;
-    HufChain H; H.left = 0;
+    RingWords ws; ws.ring0 = smem_u32(smem + CH_OFF_RING + warp * CH_RING_WARP_BYTES + lane * CH_RING_LANE_BYTES + 16); ws.gIssued = 0;
+    HufChain H; H.left = 0; H.op = nullptr; H.kNext = 0; H.hi = H.lo = 0; H.avail = 0; H.budget = 0;
     DecDesc* d = nullptr;
     u32 sh = 0;
     bool live = false, exhausted = false;
     for (;;) {
+        if (!__any_sync(0xFFFFFFFFu, !live || !H.plain())) { H.step4_fast(ws, tab, sh); continue; }
         u32 const liveMask = __ballot_sync(0xFFFFFFFFu, live);
         u32 const busyMask = __ballot_sync(0xFFFFFFFFu, live || !exhausted);
         if (!busyMask) break;
@@ -209,8 +240,8 @@ __global__ void __launch_bounds__(CH_WARPS * 32, 1) k_dec_chains(ChainsArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (warp < CH_FSE_WARPS) chains_fse_warp(a, smem, warp, lane);
-    else chains_huf_warp(a, smem, warp - CH_FSE_WARPS, warp, lane);
+    if (warp < CH_FSE_WARPS) { if (a.roles & 1) chains_fse_warp(a, smem, warp, lane); }
+    else if (a.roles & 2) chains_huf_warp(a, smem, warp - CH_FSE_WARPS, warp, lane);
 }
 
 }  // namespace zb

@@ -168,6 +168,9 @@ struct MemWords {
     ZB_HD u32 word(int k) const { return k < g.kFirst ? 0u : g.fix(k, g.W[k]); }
     ZB_HD void fetch4(int k, u32& a, u32& b, u32& c, u32& d) const { a = word(k); b = word(k - 1); c = word(k - 2); d = word(k - 3); }
     ZB_HD void advance(int) {}
+    ZB_HD u32 raw(int k) const { return word(k); }
+    ZB_HD void fetch4_fast(int k, u32& a, u32& b, u32& c, u32& d) const { fetch4(k, a, b, c, d); }
+    ZB_HD void advance_fast(int) {}
 };
 
 // ---------------------------------------------------------------------------------------- stage C
@@ -198,9 +201,14 @@ struct SeqChain {
         ws.advance(top >> 5);
     }
     // one sequence; `tLL/tOF/tML` = the frame's three tables (fse2 cells), `ct` = code tables
-    template <class WS>
-    ZB_HD void step(WS& ws, const u32* tLL, const u32* tOF, const u32* tML, const CodeTables* ct) {
-        u32 W0, W1, W2, W3; ws.fetch4(top >> 5, W0, W1, W2, W3);
+    // FAST: the caller guarantees that this is not the frame's last sequence and that the window lies above the stream's first
+    // words (no masks); the bitstream request is predicated instead of branched -- a straight line for the warp.
+    template <class WS> ZB_HD void step(WS& ws, const u32* tLL, const u32* tOF, const u32* tML, const CodeTables* ct) { step_t<false>(ws, tLL, tOF, tML, ct); }
+    template <class WS> ZB_HD void step_fast(WS& ws, const u32* tLL, const u32* tOF, const u32* tML, const CodeTables* ct) { step_t<true>(ws, tLL, tOF, tML, ct); }
+    template <bool FAST, class WS>
+    ZB_HD void step_t(WS& ws, const u32* tLL, const u32* tOF, const u32* tML, const CodeTables* ct) {
+        u32 W0, W1, W2, W3;
+        if (FAST) ws.fetch4_fast(top >> 5, W0, W1, W2, W3); else ws.fetch4(top >> 5, W0, W1, W2, W3);
         u32 const c = 31u - ((u32)top & 31u);
         u32 const V0 = fshl32(W1, W0, c), V1 = fshl32(W2, W1, c), V2 = fshl32(W3, W2, c);
         u32 const eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
@@ -213,16 +221,17 @@ struct SeqChain {
         u32 const x = shr_clamp(fshl32(V1, V0, ofBits), 32 - E);
         bool const far = q2 >= 32;
         u32 const y = shr_clamp(fshl32(far ? V2 : V1, far ? V1 : V0, q2 & 31), 32 - nTot);
-        bool const lastSeq = (k + 1 == nbSeq);
+        bool const lastSeq = !FAST && (k + 1 == nbSeq);
         top -= (int)(q2 + (lastSeq ? 0u : nTot));
-        ws.advance(top >> 5);                // the next step's four words are requested / waited for while this one finishes
+        if (FAST) ws.advance_fast(top >> 5); else ws.advance(top >> 5);      // the next step's four words are requested / waited for while this one finishes
         u32 const llc = eLL >> 25, mlc = eML >> 25;
         u32 const litLength = ct->LL_base[llc] + (x & ((1u << llBits) - 1));
         u32 const matchLength = ct->ML_base[mlc] + (x >> llBits);
         // offset / repcode history, all cases as selects: idx 0..3 = repcode slots (3: rep0 - 1), 4 = a new offset
         u32 const ll0 = (llc == 0);          // :1300 tests litLength base == 0, true for code 0 only
         u32 const idx = ofBits > 1 ? 4u : ofBits + ll0 + ofVal;
-        u32 cand = idx == 0 ? rep0 : idx == 1 ? rep1 : idx == 2 ? rep2 : idx == 3 ? rep0 - 1 : ((1u << ofBits) - 3) + ofVal;
+        u32 cand = ((1u << ofBits) - 3) + ofVal;          // selects, not branches: lanes of a warp take all five cases at once
+        cand = idx == 0 ? rep0 : cand; cand = idx == 1 ? rep1 : cand; cand = idx == 2 ? rep2 : cand; cand = idx == 3 ? rep0 - 1 : cand;
         cand -= !cand;                       // only a repcode can be zero here (rep0 - 1, or a corrupted history)
         rep2 = idx >= 2 ? rep1 : rep2; rep1 = idx >= 1 ? rep0 : rep1; rep0 = cand;
         sLL = ((eLL >> 16) & 0x1FF) + (y >> (nML + nOF));
@@ -233,6 +242,7 @@ struct SeqChain {
         ++k;
     }
     ZB_HD bool more() const { return k < nbSeq; }
+    ZB_HD bool plain() const { return k + 1 < nbSeq && (top >> 5) >= 8; }      // step_fast() may take the next sequence
     ZB_HD bool clean(u32 floorBit) const { return top + 1 == (int)floorBit; }       // every bit consumed, none borrowed
 };
 
@@ -242,7 +252,7 @@ ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables*
     MemWords ws; ws.g.set(blk + d->seqOff);
     SeqChain D;
     D.begin(ws, ws.g.floorBit, d->seqBits, d->logLL, d->logOF, d->logML, d->nbSeq, seqOut);
-    while (D.more()) D.step(ws, fse, fse + FAST_FSE_OF, fse + FAST_FSE_ML, ct);
+    while (D.more()) { if (D.plain()) D.step_fast(ws, fse, fse + FAST_FSE_OF, fse + FAST_FSE_ML, ct); else D.step(ws, fse, fse + FAST_FSE_OF, fse + FAST_FSE_ML, ct); }
     if (!D.clean(ws.g.floorBit)) d->stC = E_corruption_detected;
 }
 
@@ -293,6 +303,25 @@ struct HufChain {
         *reinterpret_cast<u32*>(op) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
         op += 4; left -= 4;
     }
+    // Straight-line form of refill() for the warp's common case (kNext above the stream's first words): the word is read
+    // and the request for the next group issued whether needed or not, selects decide what sticks.
+    template <class WS>
+    ZB_HD void refill_fast(WS& ws) {
+        bool const need = avail <= 32;
+        u32 const wv = ws.raw(kNext);
+        u32 const intoHi = shr_clamp(wv, (u32)avail), newLo = wv << ((32u - (u32)avail) & 31u);
+        hi |= need ? intoHi : 0u; lo = need ? newLo : lo;
+        avail += need ? 32 : 0; kNext -= need ? 1 : 0;
+    }
+    template <class WS>
+    ZB_HD void step4_fast(WS& ws, const u16* table, u32 sh) {
+        refill_fast(ws); u32 const s0 = symbol(table, sh), s1 = symbol(table, sh);
+        refill_fast(ws); u32 const s2 = symbol(table, sh), s3 = symbol(table, sh);
+        *reinterpret_cast<u32*>(op) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+        op += 4; left -= 4;
+        ws.advance_fast(kNext);          // at most two words, i.e. one group, further down than before
+    }
+    ZB_HD bool plain() const { return left >= 8 && aligned4() && kNext >= 8; }      // step4_fast() may take the next four symbols
     template <class WS>
     ZB_HD void step1(WS& ws, const u16* table, u32 sh) {
         refill(ws); *op++ = (u8)symbol(table, sh); left--;
@@ -308,7 +337,7 @@ ZB_HDN void dec_huf(DecDesc* d, int k, const u8* blk, const u16* huf, u8* lit) {
     HufChain H;
     H.begin(ws, ws.g.floorBit, d->sBits[k], lit + d->oOff[k], d->oCnt[k]);
     u32 const sh = 32 - d->hufLog;
-    while (H.left) { if (H.left >= 4 && H.aligned4()) H.step4(ws, huf, sh); else H.step1(ws, huf, sh); }
+    while (H.left) { if (H.plain()) H.step4_fast(ws, huf, sh); else if (H.left >= 4 && H.aligned4()) H.step4(ws, huf, sh); else H.step1(ws, huf, sh); }
     if (!H.clean()) d->stB = E_corruption_detected;
 }
 
@@ -325,9 +354,16 @@ constexpr u32 EXEC_G = 32 * EXEC_SPL;      // on a 32-lane warp
 struct alignas(16) ExecRec { u32 o, md, ls, off; };      // output start, match start, literal start, offset
 struct ExecShared {
     ExecRec rec[EXEC_G + 1];
-    u32 map[32];         // round: byte j -> 1 + index (relative to the round's first sequence) of the sequence starting there
-    u32 own[32];         // round: byte j -> that index, after the fill
+    u32 st[EXEC_G + 1 + 64];     // rec[j].o again, then 0xFFFFFFFF: the sorted array the owner searches walk
 };
+// Index (relative to `cur`) of the sequence that holds output position p: the last of st[cur .. cur+63] that is <= p.  A round of
+// 128 bytes holds at most 43 sequence starts and st[cur] <= p for every byte that is looked up, so six halving steps decide.
+ZB_HD u32 exec_owner(const u32* st, u32 p) {
+    u32 u = 0;
+    u += st[u + 32] <= p ? 32u : 0u; u += st[u + 16] <= p ? 16u : 0u; u += st[u + 8] <= p ? 8u : 0u;
+    u += st[u + 4] <= p ? 4u : 0u; u += st[u + 2] <= p ? 2u : 0u; u += st[u + 1] <= p ? 1u : 0u;
+    return u;
+}
 
 ZB_HD u32 exec_mod(u32 a, u32 b) { return a % b; }
 
@@ -393,6 +429,7 @@ ZB_HDN size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* i
             }
             ExecRec r; r.o = o; r.md = md; r.ls = ls; r.off = off[t];
             X.rec[(u32)w.lane * EXEC_SPL + t] = r;
+            X.st[(u32)w.lane * EXEC_SPL + t] = o;
             o = md + ml[t]; ls += ll[t];
         }
         u32 const badMask = w.ballot(code != 0);
@@ -402,62 +439,74 @@ ZB_HDN size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* i
         // end of the good prefix: start of sequence nGood (a sentinel record closes the table)
         u32 const endO = w.shfl(o, C::W - 1), endL = w.shfl(ls, C::W - 1);
         if (w.lane == 0 && nGood == G) { ExecRec r; r.o = endO; r.md = endO; r.ls = endL; r.off = 0; X.rec[G] = r; }
+        if (w.lane == 0) X.st[G] = endO;
+        if (badMask) for (u32 t = 0; t < EXEC_SPL; t++) { u32 const j = (u32)w.lane * EXEC_SPL + t; if (j > nGood) X.st[j] = 0xFFFFFFFFu; }      // positions after a bad sequence mean nothing: keep the array sorted
+        for (u32 j = (u32)w.lane; j < 64; j += C::W) X.st[G + 1 + j] = 0xFFFFFFFFu;
         w.sync();
         u32 const gEnd = X.rec[nGood].o;          // for nGood < G that is a real record's start
         u32 const gEndL = X.rec[nGood].ls;
-        // ---- rounds over [op, gEnd)
+        // ---- rounds over [op, gEnd): nothing in shared memory changes from here on, lanes only meet after their stores
         u32 cur = 0;                              // first sequence that is not entirely before the round
         for (u32 rb = (op + A) & ~(ROUND - 1); rb < gEnd + A; rb += ROUND) {          // rb: round start in (dst - A) coordinates
-            u32 const p0 = rb > A ? rb - A : 0;                               // first output position of the round (may precede op)
-            // map of sequence starts inside the round
-            X.map[w.lane] = 0;
-            w.sync();
-            for (u32 t = 0; t < 2; t++) {          // a round holds at most ROUND / 3 + 1 starts (43 of 64 candidates on a warp)
-                u32 const j = cur + (u32)w.lane + (u32)C::W * t;
-                if (j < nGood) { u32 const so = X.rec[j].o + A; if (so >= rb && so < rb + ROUND) reinterpret_cast<u8*>(X.map)[so - rb] = (u8)(j - cur + 1); }
+            u32 const p0 = rb > A ? rb - A : 0;                // first output position of the round (may precede op)
+            u32 const floorP = p0 > op ? p0 : op;              // sources below this are final
+            u32 const vb = rb + 4 * (u32)w.lane;               // (dst - A) coordinate of the lane's first byte
+            u32 const pb = vb - A;
+            const u32* const st = X.st + cur;
+            bool const single = st[1] + A >= rb + ROUND;       // no sequence starts inside the round after cur's own start
+            bool const interior = rb >= op + A && rb + ROUND <= gEnd + A;
+            u32 u[4] = { 0, 0, 0, 0 };                          // per byte: index (relative to cur) of the sequence it belongs to
+            if (!single) {
+                u[0] = exec_owner(st, pb);
+                u[1] = u[0] + (st[u[0] + 1] <= pb + 1 ? 1u : 0u);
+                u[2] = u[1] + (st[u[1] + 1] <= pb + 2 ? 1u : 0u);
+                u[3] = u[2] + (st[u[2] + 1] <= pb + 3 ? 1u : 0u);
             }
-            w.sync();
-            u32 const mw = X.map[w.lane];
-            // running maximum over the round = index of the sequence each byte belongs to
-            u32 b0 = mw & 0xFF, b1 = (mw >> 8) & 0xFF, b2 = (mw >> 16) & 0xFF, b3 = mw >> 24;
-            b1 = umax(b0, b1); b2 = umax(b1, b2); b3 = umax(b2, b3);
-            u32 run = b3;
-            for (int s = 1; s < C::W; s <<= 1) { u32 const t = w.shfl(run, (w.lane - s) & (C::W - 1)); if (w.lane >= s) run = umax(run, t); }
-            u32 const before = w.shfl(run, (w.lane - 1) & (C::W - 1));
-            u32 const e = w.lane ? before : 0;
-            b0 = umax(b0, e); b1 = umax(b1, e); b2 = umax(b2, e); b3 = umax(b3, e);
-            // value v > 0: sequence cur + v - 1; 0: the sequence that began before the round (cur)
-            u32 const u0 = b0 ? b0 - 1 : 0, u1 = b1 ? b1 - 1 : 0, u2 = b2 ? b2 - 1 : 0, u3 = b3 ? b3 - 1 : 0;
-            X.own[w.lane] = u0 | (u1 << 8) | (u2 << 16) | (u3 << 24);
-            w.sync();
-            u32 val = 0, validMask = 0;
+            u32 validMask = 15;
+            if (!interior) { validMask = 0; for (u32 t = 0; t < 4; t++) if (vb + t >= op + A && vb + t < gEnd + A) validMask |= 1u << t; }
+            // straight line: where every byte comes from, then the four loads together; the rare byte whose source is still being
+            // produced (an in-round source, or a match folding onto itself) takes the loop below
+            const u8* ad[4]; u32 slowMask = 0;
             for (u32 t = 0; t < 4; t++) {
-                u32 const v = rb + 4 * (u32)w.lane + t;            // (dst - A) coordinate
-                if (v < op + A || v >= gEnd + A) continue;
-                u32 p = v - A;
-                u32 const u = t == 0 ? u0 : t == 1 ? u1 : t == 2 ? u2 : u3;
-                ExecRec r = X.rec[cur + u];
-                u32 byte;
-                for (;;) {
-                    if (p < r.md) { byte = rle ? rleByte : lit[r.ls + (p - r.o)]; break; }
-                    u32 const k = p - r.md;
-                    u32 const src = r.md - r.off + (k < r.off ? k : exec_mod(k, r.off));
-                    if (src < p0 || src < op) { byte = dst[src]; break; }             // final: written before this round / this group
-                    // the source is produced in this very round: look at what produces it
-                    p = src;
-                    r = X.rec[cur + reinterpret_cast<const u8*>(X.own)[src + A - rb]];
-                }
-                val |= byte << (8 * t); validMask |= 1u << t;
+                u32 const p = pb + t;
+                ExecRec const r = X.rec[cur + u[t]];
+                bool const isLit = p < r.md;
+                u32 const src = p - r.off;
+                if (!isLit && (p - r.md >= r.off || src >= floorP)) slowMask |= 1u << t;
+                ad[t] = (isLit ? lit : dst) + (isLit ? r.ls + (p - r.o) : src);
             }
-            if (validMask == 15) *reinterpret_cast<u32*>(dstA + rb + 4 * (u32)w.lane) = val;
-            else for (u32 t = 0; t < 4; t++) if ((validMask >> t) & 1) dstA[rb + 4 * (u32)w.lane + t] = (u8)(val >> (8 * t));
-            // next round starts with the sequence holding this round's last byte (or the one after it, if it ends there)
-            u32 const lastU = w.shfl(u3, C::W - 1);
-            u32 nc = cur + lastU;
-            w.sync();
-            while (nc < nGood && X.rec[nc + 1].o + A <= rb + ROUND) nc++;     // rec[nGood] exists (sentinel or a real record)
+            slowMask &= validMask;
+            u32 val;
+            {   u32 const go = validMask & ~slowMask;
+                u32 bt[4];
+                for (u32 t = 0; t < 4; t++) bt[t] = ((go >> t) & 1) ? (u32)*ad[t] : 0u;
+                if (rle) for (u32 t = 0; t < 4; t++) if (((go >> t) & 1) && pb + t < X.rec[cur + u[t]].md) bt[t] = rleByte;
+                val = bt[0] | (bt[1] << 8) | (bt[2] << 16) | (bt[3] << 24); }
+            if (slowMask) {
+                for (u32 t = 0; t < 4; t++) {
+                    if (!((slowMask >> t) & 1)) continue;
+                    u32 p = pb + t;
+                    ExecRec r = X.rec[cur + u[t]];
+                    u32 byte;
+                    for (;;) {
+                        if (p < r.md) { byte = rle ? rleByte : lit[r.ls + (p - r.o)]; break; }
+                        u32 const k = p - r.md;
+                        u32 const src = r.md - r.off + (k < r.off ? k : exec_mod(k, r.off));
+                        if (src < floorP) { byte = dst[src]; break; }                     // final: written before this round / this group
+                        // the source is produced in this very round: look at what produces it
+                        p = src;
+                        r = X.rec[cur + exec_owner(st, src)];
+                    }
+                    val |= byte << (8 * t);
+                }
+            }
+            if (validMask == 15) *reinterpret_cast<u32*>(dstA + vb) = val;
+            else for (u32 t = 0; t < 4; t++) if ((validMask >> t) & 1) dstA[vb + t] = (u8)(val >> (8 * t));
+            // the next round starts with the sequence holding this round's last byte, or the one after it if that one ends there
+            u32 nc = cur + w.shfl(u[3], C::W - 1);
+            if (nc < nGood && X.st[nc + 1] + A <= rb + ROUND) nc++;
             cur = nc < nGood ? nc : (nGood ? nGood - 1 : 0);
-            w.sync();
+            w.sync();                                           // this round's bytes are sources of the next ones
         }
         if (failCode) return ERR((int)failCode);
         op = gEnd; lp = gEndL;
