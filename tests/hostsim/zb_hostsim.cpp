@@ -135,12 +135,15 @@ size_t zbe_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
 }
 
 // ---- the staged batch decoder (zb_decode_fast.cuh) on one item; emu != 0 runs stages A and D on the 32-lane emulator
-size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int emu) {
+size_t zbp_decompress_at(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int emu, int mis);
+size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int emu) { return zbp_decompress_at(dst, dstCapacity, src, srcSize, emu, 0); }
+// mis = 0..15: the regenerated bytes start that far off a 16-byte boundary (a batch packs its outputs back to back)
+size_t zbp_decompress_at(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int emu, int mis) {
     using namespace zb;
     DecShared* S = (DecShared*)calloc(1, sizeof(DecShared));
     u8* in = (u8*)calloc(1, srcSize + 64);
     memcpy(in + 16, src, srcSize);
-    u8* out = (u8*)calloc(1, dstCapacity + 64);
+    u8* out = (u8*)aligned_alloc(16, (dstCapacity + 96) / 16 * 16); memset(out, 0, (dstCapacity + 96) / 16 * 16);
     u8* lit = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
     u16* huf = (u16*)calloc(FAST_HUF_ENTRIES, 2);
     u32* fse = (u32*)calloc(FAST_FSE_ENTRIES, 4);
@@ -152,7 +155,7 @@ size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
     else { WarpHost w; dec_prepare(w, *S, in + 16, srcSize, dstCapacity, &d, huf, fse); }
     if (d.mode == 0) {
         u8* scratch = (u8*)calloc(1, BLOCKSIZE_MAX + 64);
-        WarpHost w; r = decompress_item(w, *S, in + 16, srcSize, out + 16, dstCapacity, scratch);
+        WarpHost w; r = decompress_item(w, *S, in + 16, srcSize, out + 16 + mis, dstCapacity, scratch);
         free(scratch);
     } else {
         const u8* blk = in + 16 + d.blockOff;
@@ -161,12 +164,12 @@ size_t zbp_decompress(void* dst, size_t dstCapacity, const void* src, size_t src
         if (getenv("ZB_DEBUG_STAGES")) fprintf(stderr, "mode %u stA1 %u stB %u stA2 %u stC %u nbSeq %u litMode %u litSize %u hufLog %u nStreams %u seqBits %u logs %u %u %u\n", d.mode, d.stA1, d.stB, d.stA2, d.stC, d.nbSeq, d.litMode, d.litSize, d.hufLog, d.nStreams, d.seqBits, d.logLL, d.logOF, d.logML);
         if (emu) {
             size_t results[32];
-            run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = dec_exec(w, *X, &d, in + 16, lit, seqs, out + 16, dstCapacity); });
+            run_warp<32>([&](const WarpEmuT<32>& w) { results[w.lane] = dec_exec(w, *X, &d, in + 16, lit, seqs, out + 16 + mis, dstCapacity); });
             r = results[0];
             for (int i = 1; i < 32; i++) if (results[i] != r) r = ERR(E_GENERIC);
-        } else { WarpHost w; r = dec_exec(w, *X, &d, in + 16, lit, seqs, out + 16, dstCapacity); }
+        } else { WarpHost w; r = dec_exec(w, *X, &d, in + 16, lit, seqs, out + 16 + mis, dstCapacity); }
     }
-    if (!isErr(r)) memcpy(dst, out + 16, r);
+    if (!isErr(r)) memcpy(dst, out + 16 + mis, r);
     free(S); free(in); free(out); free(lit); free(huf); free(fse); free(seqs); free(X);
     return r;
 }

@@ -82,6 +82,7 @@ def hostsim():
         ("zbe_compress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
         ("zbe_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         ("zbp_decompress", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]),
+        ("zbp_decompress_at", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int]),
         ("zbh_compress_params", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_uint), C.c_int]),
         ("zbh_generate_sequences", C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int]),
     ])
@@ -189,10 +190,11 @@ def emu_decompress(frame: bytes, cap: int):
     return _call_d(hostsim().zbe_decompress, frame, cap)
 
 
-def staged_decompress(frame: bytes, cap: int, emu: bool = False):
-    """The staged batch decoder (zb_decode_fast.cuh) on the host (1 lane) or on the 32-lane emulator."""
+def staged_decompress(frame: bytes, cap: int, emu: bool = False, misalign: int = 0):
+    """The staged batch decoder (zb_decode_fast.cuh) on the host (1 lane) or on the 32-lane emulator; `misalign` = distance of the
+    destination from a 16-byte boundary (a batch packs its outputs back to back)."""
     out = C.create_string_buffer(max(cap, 1))
-    n = hostsim().zbp_decompress(out, cap, frame, len(frame), 1 if emu else 0)
+    n = hostsim().zbp_decompress_at(out, cap, frame, len(frame), 1 if emu else 0, misalign)
     return out.raw[:n] if n <= ERR_MAX else -((1 << 64) - n)
 
 

@@ -107,6 +107,10 @@ def test_staged_batch_decoder_matches_oracle(emu):
     for level in (3, 1):
         for name, data in todo:
             assert staged_decompress(oracle_compress(data, level), len(data), emu) == data, (name, level)
+    # a batch packs its outputs back to back: every distance of the destination from a 4- and a 16-byte boundary
+    for mis in (1, 2, 3, 5, 14):
+        for name, data in cases.special_cases()[:8] + cases.corpus_cases(8) + cases.edge_cases(classes=(0, 5), sizes=[1, 7, 64, 255, 5000]):
+            assert staged_decompress(oracle_compress(data, 3), len(data), emu, mis) == data, (name, mis)
     man = json.loads((GOLDEN / "manifest.json").read_text())
     for e in man["decode_only"] + man["errors"]:
         blob = (GOLDEN / e["file"]).read_bytes(); cap = e.get("size", e.get("cap"))

@@ -351,10 +351,12 @@ ZB_HDN void dec_huf(DecDesc* d, int k, const u8* blk, const u16* huf, u8* lit) {
 // round is final, so no lane ever waits for another.
 constexpr u32 EXEC_SPL = 4;                  // sequences per lane and group
 constexpr u32 EXEC_G = 32 * EXEC_SPL;      // on a 32-lane warp
-struct alignas(16) ExecRec { u32 o, md, ls, off; };      // output start, match start, literal start, offset
+struct alignas(16) ExecRec { u32 o, md, ls, off; };      // output start, match start (both counted from dst - A), literal start, offset
 struct ExecShared {
     ExecRec rec[EXEC_G + 1];
     u32 st[EXEC_G + 1 + 64];     // rec[j].o again, then 0xFFFFFFFF: the sorted array the owner searches walk
+    u32 tile[32];                // a round's bytes as far as the first pass produced them ...
+    u32 late[32];                // ... and which of them it did not (bit t of word l: byte t of lane l)
 };
 // Index (relative to `cur`) of the sequence that holds output position p: the last of st[cur .. cur+63] that is <= p.  A round of
 // 128 bytes holds at most 43 sequence starts and st[cur] <= p for every byte that is looked up, so six halving steps decide.
@@ -368,7 +370,7 @@ ZB_HD u32 exec_owner(const u32* st, u32 p) {
 ZB_HD u32 exec_mod(u32 a, u32 b) { return a % b; }
 
 template <class C>
-ZB_HDN size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* item, const u8* litBuf, const u64* seqs, u8* dst, size_t cap) {
+ZB_HD size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* item, const u8* litBuf, const u64* seqs, u8* dst, size_t cap) {
     DecDesc const& d = *dp;
     if (d.mode == 2 || d.mode == 3) {            // raw / rle block: 16-byte stores once dst is aligned
         u32 const n = d.mode == 2 ? d.cSize : d.regen;
@@ -427,9 +429,9 @@ ZB_HDN size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* i
                 else if (off[t] > md) code = E_corruption_detected;
                 if (code) badAt = (u32)w.lane * EXEC_SPL + t;
             }
-            ExecRec r; r.o = o; r.md = md; r.ls = ls; r.off = off[t];
+            ExecRec r; r.o = o + A; r.md = md + A; r.ls = ls; r.off = off[t];
             X.rec[(u32)w.lane * EXEC_SPL + t] = r;
-            X.st[(u32)w.lane * EXEC_SPL + t] = o;
+            X.st[(u32)w.lane * EXEC_SPL + t] = o + A;
             o = md + ml[t]; ls += ll[t];
         }
         u32 const badMask = w.ballot(code != 0);
@@ -438,73 +440,88 @@ ZB_HDN size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* i
         if (badMask) { int const fl = (int)ctz32(badMask); nGood = w.shfl(badAt, fl); failCode = w.shfl(code, fl); }
         // end of the good prefix: start of sequence nGood (a sentinel record closes the table)
         u32 const endO = w.shfl(o, C::W - 1), endL = w.shfl(ls, C::W - 1);
-        if (w.lane == 0 && nGood == G) { ExecRec r; r.o = endO; r.md = endO; r.ls = endL; r.off = 0; X.rec[G] = r; }
-        if (w.lane == 0) X.st[G] = endO;
+        if (w.lane == 0 && nGood == G) { ExecRec r; r.o = endO + A; r.md = endO + A; r.ls = endL; r.off = 0; X.rec[G] = r; }
+        if (w.lane == 0) X.st[G] = endO + A;
         if (badMask) for (u32 t = 0; t < EXEC_SPL; t++) { u32 const j = (u32)w.lane * EXEC_SPL + t; if (j > nGood) X.st[j] = 0xFFFFFFFFu; }      // positions after a bad sequence mean nothing: keep the array sorted
         for (u32 j = (u32)w.lane; j < 64; j += C::W) X.st[G + 1 + j] = 0xFFFFFFFFu;
         w.sync();
-        u32 const gEnd = X.rec[nGood].o;          // for nGood < G that is a real record's start
+        u32 const gEndV = X.rec[nGood].o, gEnd = gEndV - A;          // for nGood < G that is a real record's start
         u32 const gEndL = X.rec[nGood].ls;
-        // ---- rounds over [op, gEnd): nothing in shared memory changes from here on, lanes only meet after their stores
+        // ---- rounds over [op, gEnd), in coordinates of (dst - A): v = position + A
+        u32 const opV = op + A;
         u32 cur = 0;                              // first sequence that is not entirely before the round
-        for (u32 rb = (op + A) & ~(ROUND - 1); rb < gEnd + A; rb += ROUND) {          // rb: round start in (dst - A) coordinates
-            u32 const p0 = rb > A ? rb - A : 0;                // first output position of the round (may precede op)
-            u32 const floorP = p0 > op ? p0 : op;              // sources below this are final
-            u32 const vb = rb + 4 * (u32)w.lane;               // (dst - A) coordinate of the lane's first byte
-            u32 const pb = vb - A;
+        for (u32 rb = opV & ~(ROUND - 1); rb < gEndV; rb += ROUND) {
+            u32 const floorV = rb > opV ? rb : opV;            // sources below this are final
+            u32 const vb = rb + 4 * (u32)w.lane;               // the lane's first byte
             const u32* const st = X.st + cur;
-            bool const single = st[1] + A >= rb + ROUND;       // no sequence starts inside the round after cur's own start
-            bool const interior = rb >= op + A && rb + ROUND <= gEnd + A;
+            bool const single = st[1] >= rb + ROUND;           // no sequence starts inside the round after cur's own start
+            bool const interior = rb >= opV && rb + ROUND <= gEndV;
             u32 u[4] = { 0, 0, 0, 0 };                          // per byte: index (relative to cur) of the sequence it belongs to
             if (!single) {
-                u[0] = exec_owner(st, pb);
-                u[1] = u[0] + (st[u[0] + 1] <= pb + 1 ? 1u : 0u);
-                u[2] = u[1] + (st[u[1] + 1] <= pb + 2 ? 1u : 0u);
-                u[3] = u[2] + (st[u[2] + 1] <= pb + 3 ? 1u : 0u);
+                u[0] = exec_owner(st, vb);
+                u[1] = u[0] + (st[u[0] + 1] <= vb + 1 ? 1u : 0u);
+                u[2] = u[1] + (st[u[1] + 1] <= vb + 2 ? 1u : 0u);
+                u[3] = u[2] + (st[u[2] + 1] <= vb + 3 ? 1u : 0u);
             }
             u32 validMask = 15;
-            if (!interior) { validMask = 0; for (u32 t = 0; t < 4; t++) if (vb + t >= op + A && vb + t < gEnd + A) validMask |= 1u << t; }
-            // straight line: where every byte comes from, then the four loads together; the rare byte whose source is still being
-            // produced (an in-round source, or a match folding onto itself) takes the loop below
-            const u8* ad[4]; u32 slowMask = 0;
+            if (!interior) { validMask = 0; for (u32 t = 0; t < 4; t++) if (vb + t >= opV && vb + t < gEndV) validMask |= 1u << t; }
+            // first pass: where every byte comes from; a match folding onto itself reads from its first period.  Bytes whose source is
+            // produced in this very round wait for the second pass.
+            const u8* ad[4]; u32 srcV[4]; u32 lateMask = 0, litMask = 0, foldMask = 0;
             for (u32 t = 0; t < 4; t++) {
-                u32 const p = pb + t;
+                u32 const v = vb + t;
                 ExecRec const r = X.rec[cur + u[t]];
-                bool const isLit = p < r.md;
-                u32 const src = p - r.off;
-                if (!isLit && (p - r.md >= r.off || src >= floorP)) slowMask |= 1u << t;
-                ad[t] = (isLit ? lit : dst) + (isLit ? r.ls + (p - r.o) : src);
+                bool const isLit = v < r.md;
+                u32 const sv = v - r.off;
+                srcV[t] = sv;
+                if (isLit) litMask |= 1u << t;
+                else { if (sv >= floorV) lateMask |= 1u << t; if (v - r.md >= r.off && r.off) foldMask |= 1u << t; }      // (records past the group's end have no offset)
+                ad[t] = isLit ? lit + (r.ls + (v - r.o)) : dstA + sv;
             }
-            slowMask &= validMask;
+            if (w.ballot(foldMask != 0)) {        // overlapping matches are rare enough for the division to live behind a vote
+                for (u32 t = 0; t < 4; t++) if ((foldMask >> t) & 1) {
+                    ExecRec const r = X.rec[cur + u[t]];
+                    u32 const sv = r.md - r.off + exec_mod(vb + t - r.md, r.off);
+                    srcV[t] = sv; ad[t] = dstA + sv;
+                    if (sv >= floorV) lateMask |= 1u << t; else lateMask &= ~(1u << t);
+                }
+            }
+            lateMask &= validMask;
             u32 val;
-            {   u32 const go = validMask & ~slowMask;
+            {   u32 const go = validMask & ~lateMask;
                 u32 bt[4];
                 for (u32 t = 0; t < 4; t++) bt[t] = ((go >> t) & 1) ? (u32)*ad[t] : 0u;
-                if (rle) for (u32 t = 0; t < 4; t++) if (((go >> t) & 1) && pb + t < X.rec[cur + u[t]].md) bt[t] = rleByte;
+                if (rle) for (u32 t = 0; t < 4; t++) if ((litMask >> t) & 1) bt[t] = rleByte;
                 val = bt[0] | (bt[1] << 8) | (bt[2] << 16) | (bt[3] << 24); }
-            if (slowMask) {
+            // second pass, only when some lane needs it: the round's bytes so far go to shared memory, a late byte takes its source from
+            // there unless that one was late too (then it walks the chain itself)
+            if (w.ballot(lateMask != 0)) {
+                X.tile[w.lane] = val; X.late[w.lane] = lateMask;
+                w.sync();
                 for (u32 t = 0; t < 4; t++) {
-                    if (!((slowMask >> t) & 1)) continue;
-                    u32 p = pb + t;
-                    ExecRec r = X.rec[cur + u[t]];
+                    if (!((lateMask >> t) & 1)) continue;
+                    u32 const j = srcV[t] - rb;                 // byte of the round that is the source
                     u32 byte;
-                    for (;;) {
-                        if (p < r.md) { byte = rle ? rleByte : lit[r.ls + (p - r.o)]; break; }
-                        u32 const k = p - r.md;
-                        u32 const src = r.md - r.off + (k < r.off ? k : exec_mod(k, r.off));
-                        if (src < floorP) { byte = dst[src]; break; }                     // final: written before this round / this group
-                        // the source is produced in this very round: look at what produces it
-                        p = src;
-                        r = X.rec[cur + exec_owner(st, src)];
+                    if (!((X.late[j >> 2] >> (j & 3)) & 1)) byte = (X.tile[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                    else {
+                        u32 v = srcV[t];
+                        for (;;) {
+                            ExecRec const r = X.rec[cur + exec_owner(st, v)];
+                            if (v < r.md) { byte = rle ? rleByte : lit[r.ls + (v - r.o)]; break; }
+                            u32 const k = v - r.md;
+                            v = r.md - r.off + (k < r.off ? k : exec_mod(k, r.off));
+                            if (v < floorV) { byte = dstA[v]; break; }
+                        }
                     }
                     val |= byte << (8 * t);
                 }
+                w.sync();
             }
             if (validMask == 15) *reinterpret_cast<u32*>(dstA + vb) = val;
             else for (u32 t = 0; t < 4; t++) if ((validMask >> t) & 1) dstA[vb + t] = (u8)(val >> (8 * t));
             // the next round starts with the sequence holding this round's last byte, or the one after it if that one ends there
             u32 nc = cur + w.shfl(u[3], C::W - 1);
-            if (nc < nGood && X.st[nc + 1] + A <= rb + ROUND) nc++;
+            if (nc < nGood && X.st[nc + 1] <= rb + ROUND) nc++;
             cur = nc < nGood ? nc : (nGood ? nGood - 1 : 0);
             w.sync();                                           // this round's bytes are sources of the next ones
         }
