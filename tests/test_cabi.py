@@ -60,6 +60,30 @@ def test_fails_loudly_without_a_device():
         Zstd.decompress(bytes.fromhex("28b52ffd2000010000"), 0)
 
 
+def test_stream_decoder_never_sizes_memory_from_the_frame_header():
+    """A 17-byte frame promising 2^40 (or 2^64-1) bytes with one empty block: the streaming layer must answer with an error code --
+    the reference streams in window-bounded memory -- instead of allocating from the header (no GPU needed: refused on the host)."""
+    from zstd_jni_b200 import _native as N
+    L = N.lib()
+    for fcs in (1 << 40, (1 << 64) - 1):
+        frame = bytes.fromhex("28b52ffd") + bytes([0xC0, 0x00]) + fcs.to_bytes(8, "little") + bytes([0x01, 0x00, 0x00])
+        z = L.ZSTD_createDStream(); L.ZSTD_initDStream(z)
+        src = C.create_string_buffer(frame, len(frame)); dst = C.create_string_buffer(1 << 16)
+        ib = N.InBuffer(C.addressof(src), len(frame), 0); ob = N.OutBuffer(C.addressof(dst), len(dst), 0)
+        r = L.ZSTD_decompressStream(z, C.byref(ob), C.byref(ib))
+        assert N.is_error(r) and N.error_code(r) == 20, r        # corruption_detected
+        L.ZSTD_freeDStream(z)
+    # batch entry points refuse sizes whose sum wraps
+    srcs = (C.c_void_p * 2)(C.addressof(src), C.addressof(src)); dsts = (C.c_void_p * 2)(C.addressof(dst), C.addressof(dst))
+    ssz = (C.c_size_t * 2)(17, 17); caps = (C.c_size_t * 2)((1 << 64) - 1, 16); outs = (C.c_size_t * 2)()
+    import torch
+    if torch.cuda.is_available():
+        ctx = L.zstdb200_create(0)
+        r = L.zstdb200_decompress_batch(ctx, 2, srcs, ssz, dsts, caps, outs)
+        assert N.is_error(r)
+        L.zstdb200_free(ctx)
+
+
 def test_missing_library_is_an_error(monkeypatch, tmp_path):
     from zstd_jni_b200 import _native
     monkeypatch.setenv("ZSTDB200_LIBRARY", str(tmp_path / "nope.so"))

@@ -148,6 +148,118 @@ def test_output_and_input_streams():                         # Zstd.scala:223-29
     assert oracle_decompress(sink.getvalue(), 0) == b""
 
 
+def _frames_of(z: bytes):
+    from zstd_jni_b200.zstd import Zstd
+    out = []; pos = 0
+    while pos < len(z):
+        n = Zstd.findFrameCompressedSize(z[pos:]); out.append(z[pos:pos + n]); pos += n
+    return out
+
+
+def test_streams_batch_whole_blocks_and_frames():
+    """The stream layer hands every whole block / frame offered in one call to the batch kernels (one launch chain per call, not per
+    block), keeps one frame per 128 KB block -- each byte-identical to the one-shot frame of that block --, writes no spurious empty
+    frame after a stream that ends on a block boundary, and reads back through both stream decoders."""
+    import numpy as np
+    from zstd_jni_b200 import corpus
+    from zstd_jni_b200.zstd import (ByteBuffer, ZstdBatchContext, ZstdDirectBufferCompressingStream, ZstdDirectBufferDecompressingStream,
+                                     ZstdInputStream, ZstdOutputStream)
+    from tests.oracle_util import oracle_compress, oracle_decompress
+    data = b"".join(corpus.chunk(i).tobytes() for i in range(24)) + corpus.chunk(3)[:50001].tobytes()      # 24 blocks + a tail
+    # ZstdOutputStream: one big write
+    sink = io.BytesIO()
+    with ZstdBatchContext(0) as probe:
+        pass
+    with ZstdOutputStream(sink, 3) as zo:
+        zo.write(data)
+    z = sink.getvalue()
+    frames = _frames_of(z)
+    assert len(frames) == 25
+    for k, f in enumerate(frames):
+        assert f == oracle_compress(data[k * 131072:(k + 1) * 131072], 3), k
+    assert oracle_decompress(z, len(data)) == data
+    # a stream that is a whole number of blocks has exactly that many frames (no empty trailer); an empty stream has one
+    sink = io.BytesIO()
+    with ZstdOutputStream(sink, 3) as zo:
+        zo.write(data[:131072])
+    assert len(_frames_of(sink.getvalue())) == 1
+    sink = io.BytesIO()
+    with ZstdOutputStream(sink, 1) as zo:
+        zo.write(data[:131072]); zo.write(data[131072:2 * 131072])
+    assert len(_frames_of(sink.getvalue())) == 2
+    # direct buffers both ways: the whole source goes to every native call
+    src = ByteBuffer.allocateDirect(len(data)); src.array[:] = np.frombuffer(data, dtype=np.uint8)
+    tgt = ByteBuffer.allocateDirect(len(data) + 4096)
+    with ZstdDirectBufferCompressingStream(tgt, 3) as zc:
+        zc.compress(src)
+    tgt.flip()
+    z2 = tgt.array[: tgt.limit()].tobytes()
+    assert z2 == z
+    back = ByteBuffer.allocateDirect(len(data) + 1)
+    zd = ZstdDirectBufferDecompressingStream(tgt)
+    while zd.hasRemaining():
+        if zd.read(back) == 0 and not back.hasRemaining():
+            break
+    zd.close()
+    assert back.position() == len(data) and back.array[: len(data)].tobytes() == data
+    # small target buffer: the pending output is handed out piecewise
+    class Drain(ZstdDirectBufferCompressingStream):
+        def __init__(self, t, lvl): super().__init__(t, lvl); self.got = []
+        def flushBuffer(self, b): b.flip(); self.got.append(b.array[: b.limit()].tobytes()); b.clear(); return b
+    small = ByteBuffer.allocateDirect(ZstdDirectBufferCompressingStream.recommendedOutputBufferSize())
+    src.position(0)
+    dr = Drain(small, 3); dr.compress(src); dr.close()
+    assert b"".join(dr.got) == z
+    # ZstdInputStream over the multi-frame stream, odd read sizes
+    with ZstdInputStream(io.BytesIO(z)) as zi:
+        got = b""
+        while True:
+            part = zi.read(333333)
+            if not part:
+                break
+            got += part
+    assert got == data
+    # a cut stream is reported, not padded
+    with ZstdInputStream(io.BytesIO(z[:-5])) as zi:
+        with pytest.raises(IOError):
+            while zi.read(1 << 20):
+                pass
+
+
+def test_async_begin_end_api_overlaps_slots():
+    """zstdb200_*_begin / _end: two batches in flight on two work sets give the same bytes as the synchronous calls."""
+    import ctypes as C
+    import numpy as np
+    from zstd_jni_b200 import corpus
+    from zstd_jni_b200.zstd import ZstdBatchContext
+    n = 48
+    a = corpus.corpus(n).reshape(-1); b = np.ascontiguousarray(a[::-1][: 40 * 131072 + 777])
+    with ZstdBatchContext(0) as ctx:
+        sa, fa = ctx.compressChunks(a, 131072, 3)
+        sb, fb = ctx.compressChunks(b, 131072, 3)
+        outA = np.empty(a.size + 65536, dtype=np.uint8); outB = np.empty(b.size + 65536, dtype=np.uint8)
+        szA = (C.c_size_t * n)(); szB = (C.c_size_t * 41)()
+        ctx.compressChunksBegin(0, a, 131072, 3)
+        ctx.compressChunksBegin(1, b, 131072, 3)
+        ta = ctx.compressChunksEnd(0, outA, szA)
+        ctx.compressChunksBegin(0, a, 131072, 1)          # slot 0 is free again while slot 1 is still out
+        tb = ctx.compressChunksEnd(1, outB, szB)
+        tc = ctx.compressChunksEnd(0, np.empty(a.size + 65536, dtype=np.uint8))
+        assert outA[:ta].tobytes() == sa.tobytes() and list(szA) == [int(x) for x in fa]
+        assert outB[:tb].tobytes() == sb.tobytes() and list(szB) == [int(x) for x in fb]
+        assert tc > 0
+        # decompression: both streams in flight
+        backA = np.empty(a.size, dtype=np.uint8); backB = np.empty(b.size, dtype=np.uint8)
+        capA = (C.c_size_t * n)(*([131072] * n)); capB = (C.c_size_t * 41)(*([131072] * 40 + [777]))
+        resA = (C.c_size_t * n)(); resB = (C.c_size_t * 41)()
+        ctx.decompressFramesBegin(2, sa, szA, backA, capA)
+        ctx.decompressFramesBegin(3, sb, szB, backB, capB)
+        ctx.decompressFramesEnd(3, resB); ctx.decompressFramesEnd(2, resA)
+        assert (backA == a).all() and (backB == b).all() and list(resB)[-1] == 777
+        with pytest.raises(Exception):
+            ctx.compressChunksEnd(2, outA)                # nothing queued on that slot: stage_wrong
+
+
 def test_input_stream_reads_reference_golden(reference_resources):   # Zstd.scala:426-446
     from zstd_jni_b200.zstd import ZstdInputStream
     xml = (reference_resources / "xml").read_bytes()

@@ -110,6 +110,12 @@ def lib() -> C.CDLL:
     sig("zstdb200_kernel_times", sz, vp, C.c_char_p, sz)
     sig("zstdb200_compress_chunks", sz, vp, i, vp, sz, sz, vp, sz, c_size_p, c_size_p)
     sig("zstdb200_decompress_frames", sz, vp, vp, c_size_p, sz, vp, sz, c_size_p)
+    sig("zstdb200_compress_chunks_begin", sz, vp, i, i, vp, sz, sz)
+    sig("zstdb200_compress_chunks_end", sz, vp, i, vp, sz, c_size_p, c_size_p)
+    sig("zstdb200_decompress_frames_begin", sz, vp, i, vp, c_size_p, sz, vp, sz, c_size_p)
+    sig("zstdb200_decompress_frames_end", sz, vp, i, c_size_p)
+    sig("zstdb200_host_register", sz, vp, sz)
+    sig("zstdb200_host_unregister", sz, vp)
     sig("zstdb200_compress_batch", sz, vp, i, sz, C.POINTER(vp), c_size_p, C.POINTER(vp), c_size_p, c_size_p)
     sig("zstdb200_decompress_batch", sz, vp, sz, C.POINTER(vp), c_size_p, C.POINTER(vp), c_size_p, c_size_p)
     sig("zstdb200_generate_sequences", sz, vp, i, sz, C.POINTER(vp), c_size_p, C.POINTER(vp), c_size_p, c_size_p)

@@ -455,6 +455,36 @@ class ZstdBatchContext(_AutoClose):
             self._raise(r)
         return out[:total], sizes
 
+    # ---- asynchronous forms (include/zstdb200.h): begin queues copy-in + kernels on work set `slot`, end collects.  The buffers are
+    # numpy uint8 arrays owned by the caller (page-locked ones make the copies asynchronous) and must stay untouched in between.
+    SLOTS = 4
+
+    def compressChunksBegin(self, slot: int, src: np.ndarray, chunkSize: int = BLOCK, level: int = 3):
+        r = N.lib().zstdb200_compress_chunks_begin(self._live(), slot, level, C.c_void_p(src.ctypes.data), src.size, chunkSize)
+        if N.is_error(r):
+            self._raise(r)
+
+    def compressChunksEnd(self, slot: int, dst: np.ndarray, frameSizes=None) -> int:
+        """Waits for slot's compression, copies the packed frames into dst; returns the stream size.  frameSizes: a ctypes size_t
+        array that receives the per-frame sizes (optional)."""
+        total = C.c_size_t(0)
+        r = N.lib().zstdb200_compress_chunks_end(self._live(), slot, C.c_void_p(dst.ctypes.data), dst.size, frameSizes, C.byref(total))
+        if N.is_error(r):
+            self._raise(r)
+        return total.value
+
+    def decompressFramesBegin(self, slot: int, stream: np.ndarray, frameSizes, dst: np.ndarray, originalSizes):
+        """frameSizes / originalSizes: ctypes size_t arrays of equal length (kept alive by the caller until End)."""
+        r = N.lib().zstdb200_decompress_frames_begin(self._live(), slot, C.c_void_p(stream.ctypes.data), frameSizes, len(frameSizes),
+                                                     C.c_void_p(dst.ctypes.data), dst.size, originalSizes)
+        if N.is_error(r):
+            self._raise(r)
+
+    def decompressFramesEnd(self, slot: int, regenerated=None):
+        r = N.lib().zstdb200_decompress_frames_end(self._live(), slot, regenerated)
+        if N.is_error(r):
+            self._raise(r)
+
     def compressBatch(self, chunks: Sequence, level: int = 3, raise_on_error: bool = True):
         L = N.lib()
         k = len(chunks)
@@ -654,3 +684,183 @@ class ZstdInputStream:
 
     def __exit__(self, *a):
         self.close()
+
+
+class ByteBuffer:
+    """The few pieces of java.nio.ByteBuffer the direct-buffer stream classes use (position / limit / remaining / flip / clear),
+    over a numpy uint8 array -- page-locked when it comes from ``allocateDirect`` (torch pinned memory when torch is importable),
+    which is what lets the copy engines take the bytes without a staging pass, like a registered DirectByteBuffer."""
+
+    def __init__(self, array: np.ndarray):
+        assert array.dtype == np.uint8 and array.ndim == 1 and array.flags["C_CONTIGUOUS"]
+        self.array = array
+        self._position = 0
+        self._limit = array.size
+        self._keep = None
+
+    @staticmethod
+    def allocateDirect(capacity: int) -> "ByteBuffer":
+        try:
+            import torch
+            t = torch.empty(capacity, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+            b = ByteBuffer(t.numpy()); b._keep = t
+            return b
+        except ImportError:
+            return ByteBuffer(np.empty(capacity, dtype=np.uint8))
+
+    @staticmethod
+    def wrap(data) -> "ByteBuffer":
+        return ByteBuffer(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+
+    def isDirect(self) -> bool: return True
+    def capacity(self) -> int: return self.array.size
+    def position(self, p: int | None = None):
+        if p is None: return self._position
+        assert 0 <= p <= self._limit; self._position = p; return self
+    def limit(self, l: int | None = None):
+        if l is None: return self._limit
+        assert 0 <= l <= self.array.size; self._limit = l; self._position = min(self._position, l); return self
+    def remaining(self) -> int: return self._limit - self._position
+    def hasRemaining(self) -> bool: return self._position < self._limit
+    def flip(self): self._limit = self._position; self._position = 0; return self
+    def clear(self): self._position = 0; self._limit = self.array.size; return self
+    def address(self) -> int: return self.array.ctypes.data
+
+
+class ZstdDirectBufferCompressingStream:
+    """J/ZstdDirectBufferCompressingStreamNoFinalizer.java:13-200 over ZSTD_compressStream / flushStream / endStream
+    (N/jni_directbuffercompress_zstd.c): the whole remaining source goes to every native call, so the batch path behind
+    ZSTD_compressStream2 sees hundreds of MiB at a time.  ``flushBuffer`` is the hook a subclass overrides to drain the target."""
+
+    def __init__(self, target: ByteBuffer, level: int = 3):
+        L = N.lib()
+        self._target = target
+        self._z = L.ZSTD_createCStream()
+        self._level = level
+        self._initialized = False
+        self._closed = False
+
+    @staticmethod
+    def recommendedOutputBufferSize() -> int:
+        return int(N.lib().ZSTD_CStreamOutSize())
+
+    def flushBuffer(self, toFlush: ByteBuffer) -> ByteBuffer:
+        return toFlush
+
+    def _call(self, src: ByteBuffer | None, end_op: int) -> int:
+        L = N.lib()
+        t = self._target
+        ib = N.InBuffer(src.address() + src.position() if src is not None else 0, src.remaining() if src is not None else 0, 0)
+        ob = N.OutBuffer(t.address() + t.position(), t.remaining(), 0)
+        r = L.ZSTD_compressStream2(self._z, C.byref(ob), C.byref(ib), end_op)
+        if N.is_error(r):
+            raise ZstdException(N.error_code(r), L.ZSTD_getErrorName(r).decode())
+        t.position(t.position() + ob.pos)
+        if src is not None:
+            src.position(src.position() + ib.pos)
+        return r
+
+    def compress(self, source: ByteBuffer):
+        if self._closed:
+            raise IOError("Stream closed")
+        if not self._initialized:
+            N.lib().ZSTD_initCStream(self._z, self._level); self._initialized = True
+        while source.hasRemaining():
+            if not self._target.hasRemaining():
+                self._target = self.flushBuffer(self._target)
+                if not self._target.hasRemaining():
+                    raise IOError("The target buffer has no more space, even after flushing, and there are still bytes to compress")
+            self._call(source, ZSTD_e_continue)
+
+    def _finish(self, end_op: int):
+        if not self._initialized:
+            return
+        first = True
+        while True:
+            needed = self._call(None, end_op)
+            self._target = self.flushBuffer(self._target)
+            if needed > 0 and not self._target.hasRemaining() and not first:
+                raise IOError("The target buffer has no more space, even after flushing, and there are still bytes to compress")
+            first = False
+            if needed == 0:
+                break
+
+    def flush(self):
+        if self._closed:
+            raise IOError("Already closed")
+        self._finish(ZSTD_e_flush)
+
+    def close(self):
+        if self._closed:
+            return
+        try:
+            self._finish(ZSTD_e_end)
+        finally:
+            N.lib().ZSTD_freeCStream(self._z)
+            self._closed = True
+            self._target = None
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
+
+
+class ZstdDirectBufferDecompressingStream:
+    """J/ZstdDirectBufferDecompressingStreamNoFinalizer.java + J/BaseZstdBufferDecompressingStreamNoFinalizer.java:76-112 over
+    ZSTD_decompressStream (N/jni_directbufferdecompress_zstd.c).  ``refill`` is the subclass hook that supplies more source."""
+
+    def __init__(self, source: ByteBuffer):
+        L = N.lib()
+        self._source = source
+        self._z = L.ZSTD_createDStream()
+        L.ZSTD_initDStream(self._z)
+        self._closed = False
+        self._streamEnd = False
+        self._finishedFrame = False
+
+    @staticmethod
+    def recommendedTargetBufferSize() -> int:
+        return int(N.lib().ZSTD_DStreamOutSize())
+
+    def refill(self, toRefill: ByteBuffer) -> ByteBuffer:
+        return toRefill
+
+    def hasRemaining(self) -> bool:
+        return self._source is not None and not self._closed and not self._streamEnd and (self._source.hasRemaining() or not self._finishedFrame)
+
+    def setLongMax(self, windowLogMax: int):
+        if self._closed:
+            raise IOError("Stream closed")
+        r = N.lib().ZSTD_DCtx_setParameter(self._z, ZSTD_d_windowLogMax, windowLogMax)
+        if N.is_error(r):
+            raise ZstdException(N.error_code(r), N.lib().ZSTD_getErrorName(r).decode())
+        return self
+
+    def read(self, target: ByteBuffer) -> int:
+        if self._closed:
+            raise IOError("Stream closed")
+        if self._streamEnd:
+            return 0
+        L = N.lib()
+        s = self._source
+        ib = N.InBuffer(s.address() + s.position(), s.remaining(), 0)
+        ob = N.OutBuffer(target.address() + target.position(), target.remaining(), 0)
+        remaining = L.ZSTD_decompressStream(self._z, C.byref(ob), C.byref(ib))
+        if N.is_error(remaining):
+            raise ZstdException(N.error_code(remaining), L.ZSTD_getErrorName(remaining).decode())
+        s.position(s.position() + ib.pos)
+        target.position(target.position() + ob.pos)
+        if not s.hasRemaining():
+            self._source = s = self.refill(s)
+        self._finishedFrame = remaining == 0
+        if self._finishedFrame:
+            self._streamEnd = not s.hasRemaining()
+        return ob.pos
+
+    def close(self):
+        if not self._closed:
+            N.lib().ZSTD_freeDStream(self._z)
+            self._closed = True
+            self._source = None
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
