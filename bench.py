@@ -561,54 +561,56 @@ def strong_scaling(args, ctx, L, dev, rank, world, local, check, barrier):
     d_back = torch.empty(max(cnt, 1) * CHUNK, dtype=torch.uint8, device=dev); d_res = torch.zeros(max(cnt, 1), dtype=torch.int64, device=dev)
     stream_root = torch.empty(n_total * stride, dtype=torch.uint8, device=dev) if rank == 0 else None
     back_root = torch.empty(n_total * CHUNK, dtype=torch.uint8, device=dev) if rank == 0 else None
-    cur = torch.cuda.current_stream(dev); st = cur.cuda_stream
+    cur = torch.cuda.Stream(device=dev); st = cur.cuda_stream        # an explicit stream: 0 would mean "the context's own stream" to the C ABI
     rec = {"total_bytes": n_total * CHUNK, "n_gpus": world, "levels": {}}
-    for lvl in (1, 3, 9):
-        def run(timed):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-            ev[0].record(cur)
-            sharding.scatter_chunks(batch, n_total, CHUNK, mine)
-            ev[1].record(cur)
-            check(L.zstdb200_compress_device(ctx.handle, lvl, cnt, mine.data_ptr(), d_off.data_ptr(), d_slots.data_ptr(), stride, d_sizes.data_ptr(), st))
-            check(L.zstdb200_compact_device(ctx.handle, cnt, d_slots.data_ptr(), stride, d_sizes.data_ptr(), d_out.data_ptr(), d_ooff.data_ptr(), st))
-            ev[2].record(cur)
-            offs = sharding.global_offsets(sharding.gather_sizes(d_sizes[:cnt], n_total))
-            ranges = sharding.rank_byte_ranges(offs, n_total, world)
-            sharding.gatherv_bytes(d_out, ranges, stream_root)
-            ev[3].record(cur)
-            # way back: the root deals the frames' byte ranges out again, ranks decode, chunks come home
-            lo, hi = ranges[rank]
-            frames_local = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=dev)
-            ops = []
-            if rank == 0:
-                frames_local[: hi - lo].copy_(stream_root[lo:hi])
-                for r in range(1, world):
-                    if ranges[r][1] > ranges[r][0]: ops.append(dist.P2POp(dist.isend, stream_root[ranges[r][0]:ranges[r][1]], r))
-            elif hi > lo:
-                ops.append(dist.P2POp(dist.irecv, frames_local[: hi - lo], 0))
-            if ops:
-                for w in dist.batch_isend_irecv(ops): w.wait()
-            loc_off = (offs[s:e + 1] - offs[s]).contiguous()
-            ev[4].record(cur)
-            check(L.zstdb200_decompress_device(ctx.handle, cnt, frames_local.data_ptr(), loc_off.data_ptr(), d_back.data_ptr(), d_off.data_ptr(), d_res.data_ptr(), st))
-            sharding.gather_fixed(d_back, n_total, CHUNK, back_root)
-            ev[5].record(cur)
-            torch.cuda.synchronize()
-            t = [ev[k].elapsed_time(ev[k + 1]) for k in range(5)]
-            return t, int(offs[-1])
-        run(False); barrier()
-        t, csize = run(True)
-        tt = torch.tensor(t, dtype=torch.float64, device=dev)
-        if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t = [float(x) for x in tt.tolist()]
-        ok = True
-        if rank == 0:
-            ok = bool(torch.equal(back_root, batch))
-        rec["levels"][f"L{lvl}"] = {"scatter_ms": t[0], "compress_ms": t[1], "sizes+gatherv_ms": t[2], "frames_scatter_ms": t[3], "decompress+gather_ms": t[4],
-                                     "compress_path_ms": t[0] + t[1] + t[2], "round_trip_ms": sum(t), "compressed_bytes": csize,
-                                     "compress_gbs": n_total * CHUNK / ((t[0] + t[1] + t[2]) * 1e-3) / 1e9, "round_trip_gbs": n_total * CHUNK / (sum(t) * 1e-3) / 1e9,
-                                     "limiting": max((("scatter", t[0]), ("k_parse+k_entropy (per-frame tail)", t[1]), ("gatherv", t[2]), ("frames scatter", t[3]), ("decode+gather", t[4])), key=lambda kv: kv[1])[0],
-                                     "verified": ok}
+    torch.cuda.synchronize()
+    with torch.cuda.stream(cur):
+      for lvl in (1, 3, 9):
+          def run(timed):
+              ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+              ev[0].record(cur)
+              sharding.scatter_chunks(batch, n_total, CHUNK, mine)
+              ev[1].record(cur)
+              check(L.zstdb200_compress_device(ctx.handle, lvl, cnt, mine.data_ptr(), d_off.data_ptr(), d_slots.data_ptr(), stride, d_sizes.data_ptr(), st))
+              check(L.zstdb200_compact_device(ctx.handle, cnt, d_slots.data_ptr(), stride, d_sizes.data_ptr(), d_out.data_ptr(), d_ooff.data_ptr(), st))
+              ev[2].record(cur)
+              offs = sharding.global_offsets(sharding.gather_sizes(d_sizes[:cnt], n_total))
+              ranges = sharding.rank_byte_ranges(offs, n_total, world)
+              sharding.gatherv_bytes(d_out, ranges, stream_root)
+              ev[3].record(cur)
+              # way back: the root deals the frames' byte ranges out again, ranks decode, chunks come home
+              lo, hi = ranges[rank]
+              frames_local = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=dev)
+              ops = []
+              if rank == 0:
+                  frames_local[: hi - lo].copy_(stream_root[lo:hi])
+                  for r in range(1, world):
+                      if ranges[r][1] > ranges[r][0]: ops.append(dist.P2POp(dist.isend, stream_root[ranges[r][0]:ranges[r][1]], r))
+              elif hi > lo:
+                  ops.append(dist.P2POp(dist.irecv, frames_local[: hi - lo], 0))
+              if ops:
+                  for w in dist.batch_isend_irecv(ops): w.wait()
+              loc_off = (offs[s:e + 1] - offs[s]).contiguous()
+              ev[4].record(cur)
+              check(L.zstdb200_decompress_device(ctx.handle, cnt, frames_local.data_ptr(), loc_off.data_ptr(), d_back.data_ptr(), d_off.data_ptr(), d_res.data_ptr(), st))
+              sharding.gather_fixed(d_back, n_total, CHUNK, back_root)
+              ev[5].record(cur)
+              torch.cuda.synchronize()
+              t = [ev[k].elapsed_time(ev[k + 1]) for k in range(5)]
+              return t, int(offs[-1])
+          run(False); barrier()
+          t, csize = run(True)
+          tt = torch.tensor(t, dtype=torch.float64, device=dev)
+          if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+          t = [float(x) for x in tt.tolist()]
+          ok = True
+          if rank == 0:
+              ok = bool(torch.equal(back_root, batch))
+          rec["levels"][f"L{lvl}"] = {"scatter_ms": t[0], "compress_ms": t[1], "sizes+gatherv_ms": t[2], "frames_scatter_ms": t[3], "decompress+gather_ms": t[4],
+                                       "compress_path_ms": t[0] + t[1] + t[2], "round_trip_ms": sum(t), "compressed_bytes": csize,
+                                       "compress_gbs": n_total * CHUNK / ((t[0] + t[1] + t[2]) * 1e-3) / 1e9, "round_trip_gbs": n_total * CHUNK / (sum(t) * 1e-3) / 1e9,
+                                       "limiting": max((("scatter", t[0]), ("k_parse+k_entropy (per-frame tail)", t[1]), ("gatherv", t[2]), ("frames scatter", t[3]), ("decode+gather", t[4])), key=lambda kv: kv[1])[0],
+                                       "verified": ok}
     rec["note"] = "strong scaling: efficiency(N) = round_trip_gbs(N) / (N x round_trip_gbs(1)) is computed by the reader from the per-N lines; N = 1 runs the same code without peers"
     return rec
 

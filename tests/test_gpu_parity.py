@@ -92,6 +92,57 @@ def test_decoder_matches_oracle_on_corruptions(ctx):
         assert e == g, (k, e if isinstance(e, int) else "ok", g if isinstance(g, int) else "ok")
 
 
+def _literal_payload(z: bytes):
+    """(first, end) byte range of the compressed-literals payload (Huffman tree description + streams) of a one-block frame, or None."""
+    fhd = z[4]; single = (fhd >> 5) & 1; fcs = fhd >> 6; did = fhd & 3
+    pos = 5 + (0 if single else 1) + (4 if did == 3 else did) + ((1 << fcs) if fcs else (1 if single else 0))
+    bh = z[pos] | (z[pos + 1] << 8) | (z[pos + 2] << 16)
+    if (bh >> 1) & 3 != 2:
+        return None
+    blk = pos + 3
+    b0 = z[blk]; typ = b0 & 3; lhl = (b0 >> 2) & 3
+    if typ < 2:
+        return None
+    lhc = int.from_bytes(z[blk:blk + 5], "little")
+    if lhl < 2: lh, csz = 3, (lhc >> 14) & 0x3FF
+    elif lhl == 2: lh, csz = 4, (lhc >> 18) & 0x3FFF
+    else: lh, csz = 5, (lhc >> 22) & 0x3FFFF
+    return blk + lh, blk + lh + csz
+
+
+@pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
+def test_decoder_matches_the_compiled_reference_on_corruptions(ctx):
+    """The same single-bit corruptions judged by the reference itself (oracle/_ref), not by the restatement.  One class of input is
+    allowed to differ, exactly as DESIGN.md section 5 documents it: a flipped bit INSIDE the compressed-literals payload, where this
+    decoder demands that every Huffman stream ends on its first bit (corruption_detected) while the reference's fast 4-stream loop
+    (N/decompress/huf_decompress.c:219,236,281-300,840-893) may hand back bytes or a later error.  Anything else must agree."""
+    from zstd_jni_b200 import corpus
+    from tests.oracle_util import ref_decompress
+    rng = np.random.default_rng(11)
+    blobs, caps, exp, where, hdr = [], [], [], [], []
+    for idx in (0, 1, 2, 3, 4, 5, 7, 9):
+        data = corpus.chunk(idx)[:60000].tobytes()
+        for level in (3, 1):
+            z = ref_compress(data, level)
+            lit = _literal_payload(z)
+            for _ in range(40):
+                zz = bytearray(z)
+                k = int(rng.integers(0, len(zz))); zz[k] ^= 1 << int(rng.integers(0, 8))
+                blobs.append(bytes(zz)); caps.append(len(data)); exp.append(ref_decompress(bytes(zz), len(data)))
+                where.append(lit is not None and lit[0] <= k < lit[1]); hdr.append(4 <= k < 9)
+    got = ctx.decompressBatch(blobs, caps, raise_on_error=False)
+    allowed = header = 0
+    for k, (e, g) in enumerate(zip(exp, got)):
+        if e == g:
+            continue
+        if hdr[k] and isinstance(e, int) and isinstance(g, int) and {e, g} <= {-20, -70}:
+            header += 1          # second documented class: a damaged content-size / window field; the reference trips over its literal-buffer
+            continue             # placement inside dst (dstSize_tooSmall), this decoder over the size check (corruption_detected) or vice versa
+        assert where[k] and g == -20, (k, e if isinstance(e, int) else "bytes", g if isinstance(g, int) else "bytes")
+        allowed += 1
+    assert allowed <= len(blobs) // 4 and header <= len(blobs) // 50, (allowed, header)        # minorities (~8 % and < 1 % of random flips)
+
+
 @pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
 def test_decodes_reference_streams(ctx):
     from zstd_jni_b200 import corpus

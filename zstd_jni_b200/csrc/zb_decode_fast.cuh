@@ -455,6 +455,48 @@ ZB_HD size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* it
             u32 const vb = rb + 4 * (u32)w.lane;               // the lane's first byte
             const u32* const st = X.st + cur;
             bool const single = st[1] >= rb + ROUND;           // no sequence starts inside the round after cur's own start
+            // Long runs first: when this round and at least three more lie inside ONE literal run, or inside one match whose source
+            // is far enough back (or repeats with a period of 1, 2 or 4 bytes), the bytes are moved as aligned words -- four per
+            // lane and iteration, 512 bytes per warp iteration, each store instruction one contiguous 128-byte line -- without any
+            // per-byte bookkeeping.  Everything shorter, nearer or odd goes through the rounds below.
+            if (C::W == 32 && single && rb >= opV) {
+                ExecRec const r = X.rec[cur];
+                bool const inLit = rb + ROUND <= r.md, inMatch = rb >= r.md;
+                u32 const segEnd = inLit ? r.md : (st[1] < gEndV ? st[1] : gEndV);
+                u32 const span = (inLit || inMatch) && segEnd > rb ? ((segEnd - rb) & ~511u) : 0;
+                bool const periodic = inMatch && (r.off == 1 || r.off == 2 || r.off == 4);
+                if (span && (inLit ? true : (r.off >= 512 || periodic))) {
+                    if ((inLit && rle) || periodic) {
+                        u32 pat;
+                        if (inLit) pat = rleByte * 0x01010101u;
+                        else {      // the period starts at md - off; a 4-aligned v has the same phase everywhere because off divides 4
+                            u32 const ph = (rb - r.md) & (r.off - 1);
+                            pat = 0;
+                            for (u32 j = 0; j < 4; j++) pat |= (u32)dstA[r.md - r.off + ((ph + j) & (r.off - 1))] << (8 * j);
+                        }
+                        for (u32 it = rb; it < rb + span; it += 512)
+                            for (u32 j = 0; j < 4; j++) *reinterpret_cast<u32*>(dstA + it + 128 * j + 4 * (u32)w.lane) = pat;
+                    } else {
+                        const u8* const sb = inLit ? lit + (r.ls + (rb - r.o)) : dstA + (rb - r.off);      // source of byte rb
+                        for (u32 it = rb; it < rb + span; it += 512) {
+                            u32 wv[4];
+                            for (u32 j = 0; j < 4; j++) {
+                                const u8* const sp = sb + (it - rb) + 128 * j + 4 * (u32)w.lane;
+                                uintptr_t const a = reinterpret_cast<uintptr_t>(sp);
+                                u32 const sh = (u32)(a & 3) * 8;
+                                const u32* const aw = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+                                u32 const w0 = aw[0], w1 = sh ? aw[1] : 0u;
+                                wv[j] = fshr32(w0, w1, sh);
+                            }
+                            for (u32 j = 0; j < 4; j++) *reinterpret_cast<u32*>(dstA + it + 128 * j + 4 * (u32)w.lane) = wv[j];
+                            if (!inLit) w.sync();               // a far match may still read what the previous iteration wrote
+                        }
+                    }
+                    rb += span - ROUND;                         // (the loop adds the last ROUND)
+                    w.sync();
+                    continue;                                   // cur is unchanged: the run ended inside the same sequence
+                }
+            }
             bool const interior = rb >= opV && rb + ROUND <= gEndV;
             u32 u[4] = { 0, 0, 0, 0 };                          // per byte: index (relative to cur) of the sequence it belongs to
             if (!single) {
