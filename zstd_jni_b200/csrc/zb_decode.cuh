@@ -27,6 +27,7 @@ struct DecShared {
     u32 sLit[SEQ_BATCH], sMatch[SEQ_BATCH], sOff[SEQ_BATCH];
     i16 norm[3][64];
     u16 symNext[3][64];
+    u16 cum[66];            // cumulative cell counts of the table being built (build_fse_dtable_warp)
     u8 spread[3][512];
     u8 weights[256];
     u32 wdt[64];            // FSE decode table of the Huffman-weight stream (tableLog <= 6)
@@ -130,6 +131,69 @@ ZB_HDN bool build_fse_dtable(u32* table, const i16* norm, u32 maxSV, u32 tableLo
         u32 const ns = symNext[s]++;
         u32 const nb = tableLog - highbit32(ns);
         table[u] = (((ns << nb) - tableSize) & 0xFFFFu) | (nb << 16) | (s << 24);
+    }
+    return true;
+}
+
+// The same table built by all lanes of the warp (sequence tables: maxSV <= 52, tableLog <= 9).  Nothing about the result
+// changes; the three serial loops of the reference become data-parallel steps:
+//   * the spread visits positions (j * step) & mask for j = 0, 1, 2 ... and skips the cells above `high` (those belong to the
+//     low-probability symbols), so the k-th visited cell takes the symbol whose cumulative count range holds k -- lanes take 32
+//     consecutive j, rank themselves with a ballot and look the symbol up in the cumulative counts;
+//   * the state numbering hands the cells of one symbol consecutive numbers in cell order -- lanes take 32 consecutive cells,
+//     lanes with the same symbol rank themselves with match_any, the first of them advances the symbol's counter.
+template <class C>
+ZB_HDN bool build_fse_dtable_warp(const C& w, u32* table, const i16* norm, u32 maxSV, u32 tableLog, u16* symNext, u8* spread, u16* cum) {
+    u32 const tableSize = 1u << tableLog, mask = tableSize - 1;
+    u32 const step = (tableSize >> 1) + (tableSize >> 3) + 3;
+    u32 const lane = (u32)w.lane, below = (1u << lane) - 1;
+    // low-probability symbols from the top down, cumulative counts of the others
+    u32 nLow = 0, total = 0;
+    for (u32 s0 = 0; s0 <= maxSV; s0 += C::W) {
+        u32 const sy = s0 + lane;
+        int const n = sy <= maxSV ? (int)norm[sy] : 0;
+        u32 const lowM = w.ballot(n == -1);
+        if (n == -1) { spread[tableSize - 1 - nLow - popc32(lowM & below)] = (u8)sy; symNext[sy] = 1; }
+        else if (sy <= maxSV) symNext[sy] = (u16)n;
+        u32 const cnt = n > 0 ? (u32)n : 0;
+        u32 const before = w.exscan(cnt);
+        if (sy <= maxSV) cum[sy] = (u16)(total + before);
+        total += w.sum(cnt); nLow += popc32(lowM);
+    }
+    u32 const high = tableSize - 1 - nLow;
+    for (u32 sy = maxSV + 1 + lane; sy < 66; sy += C::W) cum[sy] = 0xFFFF;      // sentinels for the search
+    w.sync();
+    if (total != high + 1) return false;                   // the distribution does not tile the table (reference: pos != 0 after the spread)
+    u32 kBase = 0;
+    for (u32 j0 = 0; j0 < tableSize; j0 += C::W) {
+        u32 const j = j0 + lane;
+        u32 const pos = (j * step) & mask;
+        bool const valid = j < tableSize && pos <= high;
+        u32 const vm = w.ballot(valid);
+        if (valid) {
+            u32 const k = kBase + popc32(vm & below);
+            u32 sy = 0;                                        // last symbol with cum[sy] <= k (cum is non-decreasing; 64 entries + sentinels)
+            sy += cum[sy + 32] <= k ? 32u : 0u; sy += cum[sy + 16] <= k ? 16u : 0u; sy += cum[sy + 8] <= k ? 8u : 0u;
+            sy += cum[sy + 4] <= k ? 4u : 0u; sy += cum[sy + 2] <= k ? 2u : 0u; sy += cum[sy + 1] <= k ? 1u : 0u;
+            spread[pos] = (u8)sy;
+        }
+        kBase += popc32(vm);
+    }
+    w.sync();
+    for (u32 u0 = 0; u0 < tableSize; u0 += C::W) {
+        u32 const u = u0 + lane;
+        bool const on = u < tableSize;
+        u32 const sy = on ? spread[u] : 0xFFFFFFFFu - lane;
+        u32 const same = w.match_any(sy);
+        u32 const base = on ? symNext[sy] : 0;
+        w.sync();
+        if (on) {
+            u32 const ns = base + popc32(same & below);
+            u32 const nb = tableLog - highbit32(ns);
+            table[u] = (((ns << nb) - tableSize) & 0xFFFFu) | (nb << 16) | (sy << 24);
+            if (!(same & below)) symNext[sy] = (u16)(base + popc32(same));
+        }
+        w.sync();
     }
     return true;
 }
@@ -414,21 +478,22 @@ ZB_HDN size_t parse_seq_section(const C& w, DecShared& S, const u8* ip, size_t l
     if (isErr(hdr)) return hdr;
     if (nbSeq) {
         if (cap == 0) return ERR(E_dstSize_tooSmall);
-        // table construction: one lane per table (ZSTD_buildSeqTable :647-693)
-        for (int t = w.lane; t < 3; t += C::W) {
+        // table construction, all lanes on one table after the other (ZSTD_buildSeqTable :647-693)
+        for (int t = 0; t < 3; t++) {
             u32 const mode = S.fseMode[t];
-            if (mode == 1) { S.fse[t][0] = (S.fseMax[t] << 24); S.fseLog[t] = 0; }
+            if (mode == 1) { if (w.lane == 0) { S.fse[t][0] = (S.fseMax[t] << 24); S.fseLog[t] = 0; } }
             else if (mode == 0) {
                 const i16* dn = t == 0 ? ZB_T.LL_defaultNorm : t == 1 ? ZB_T.OF_defaultNorm : ZB_T.ML_defaultNorm;
                 u32 const dmax = t == 0 ? MaxLL : t == 1 ? DefaultMaxOff : MaxML, dlog = t == 1 ? 5 : 6;
-                for (u32 s = 0; s <= dmax; s++) S.norm[t][s] = dn[s];
-                build_fse_dtable(S.fse[t], S.norm[t], dmax, dlog, S.symNext[t], S.spread[t]);
-                S.fseLog[t] = dlog;
+                for (u32 sy = (u32)w.lane; sy <= dmax; sy += C::W) S.norm[t][sy] = dn[sy];
+                w.sync();
+                build_fse_dtable_warp(w, S.fse[t], S.norm[t], dmax, dlog, S.symNext[t], S.spread[t], S.cum);
+                if (w.lane == 0) S.fseLog[t] = dlog;
             } else if (mode == 2) {
-                build_fse_dtable(S.fse[t], S.norm[t], S.fseMax[t], S.fseLog[t], S.symNext[t], S.spread[t]);
+                build_fse_dtable_warp(w, S.fse[t], S.norm[t], S.fseMax[t], S.fseLog[t], S.symNext[t], S.spread[t], S.cum);
             }
+            w.sync();
         }
-        w.sync();
     }
     *nbSeqOut = nbSeq;
     return hdr;

@@ -509,24 +509,15 @@ ZB_HD size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* it
             if (!interior) { validMask = 0; for (u32 t = 0; t < 4; t++) if (vb + t >= opV && vb + t < gEndV) validMask |= 1u << t; }
             // first pass: where every byte comes from; a match folding onto itself reads from its first period.  Bytes whose source is
             // produced in this very round wait for the second pass.
-            const u8* ad[4]; u32 srcV[4]; u32 lateMask = 0, litMask = 0, foldMask = 0;
+            const u8* ad[4]; u32 srcV[4]; u32 lateMask = 0, litMask = 0;
             for (u32 t = 0; t < 4; t++) {
                 u32 const v = vb + t;
                 ExecRec const r = X.rec[cur + u[t]];
                 bool const isLit = v < r.md;
-                u32 const sv = v - r.off;
+                u32 const sv = v - r.off;          // a match that overlaps itself may read `offset` back as long as that byte is final
                 srcV[t] = sv;
-                if (isLit) litMask |= 1u << t;
-                else { if (sv >= floorV) lateMask |= 1u << t; if (v - r.md >= r.off && r.off) foldMask |= 1u << t; }      // (records past the group's end have no offset)
+                if (isLit) litMask |= 1u << t; else if (sv >= floorV) lateMask |= 1u << t;
                 ad[t] = isLit ? lit + (r.ls + (v - r.o)) : dstA + sv;
-            }
-            if (w.ballot(foldMask != 0)) {        // overlapping matches are rare enough for the division to live behind a vote
-                for (u32 t = 0; t < 4; t++) if ((foldMask >> t) & 1) {
-                    ExecRec const r = X.rec[cur + u[t]];
-                    u32 const sv = r.md - r.off + exec_mod(vb + t - r.md, r.off);
-                    srcV[t] = sv; ad[t] = dstA + sv;
-                    if (sv >= floorV) lateMask |= 1u << t; else lateMask &= ~(1u << t);
-                }
             }
             lateMask &= validMask;
             u32 val;
