@@ -1,8 +1,14 @@
 // zb_decode_chains.cuh -- device side of stages B + C of the staged decoder (zb_decode_fast.cuh): k_dec_chains.
 //
-// One persistent CTA per SM, four warps, each on its own scheduler:
-//   warps 0 .. CH_FSE_WARPS-1        sequence chains: CH_FSE_LANES lanes per warp, one frame per lane (SeqChain)
-//   warps CH_FSE_WARPS .. CH_WARPS-1 Huffman chains: 8 frames x 4 streams per warp (HufChain)
+// One persistent CTA per SM, six warps:
+//   warps 0 .. 1   Huffman chains: 8 frames x 4 streams per warp (HufChain)
+//   warps 2 .. 3   sequence chains, WALK half: CH_FSE_LANES lanes per warp, one frame per lane (SeqChain::walk) -- each alone
+//                  on its scheduler, because a chain is as fast as its warp issues
+//   warps 4 .. 5   sequence chains, VALUE half (SeqValue::take): lane l of warp 4 + w finishes what lane l of warp 2 + w
+//                  walks; they share the schedulers of the Huffman warps, which mostly wait
+// A walk lane hands its value lane 16-byte raw records through a 16-deep ring in shared memory: one 128-bit store / load each,
+// a generation bit inside the record is the only flag (no fences on the chain), the value lane reports its progress every
+// fourth record and the walk lane looks at that report before it could lap the ring.  Frame changes go through a small mailbox.
 // Lanes are persistent: a lane (a group of 4 lanes for Huffman) that finishes its frame draws the next one from a
 // longest-first work list while the other lanes keep stepping, so the kernel lasts (total steps / lanes) or as long
 // as its longest chain, whichever is more -- not (waves x longest chain).
@@ -21,13 +27,16 @@
 namespace zb {
 
 constexpr int CH_FSE_WARPS = 2, CH_FSE_LANES = 14, CH_HUF_WARPS = 2;
-constexpr int CH_WARPS = CH_FSE_WARPS + CH_HUF_WARPS;
+constexpr int CH_WARPS = CH_HUF_WARPS + 2 * CH_FSE_WARPS;      // Huffman | walk | value
+constexpr u32 CH_LINK_DEPTH = 16;                               // raw records between a walk lane and its value lane
+constexpr u32 CH_LINK_BYTES = CH_LINK_DEPTH * 16 + 32;          // ring + mailbox
 constexpr int CH_RING_GROUPS = 8;        // 16-byte cells per lane ring
 constexpr int CH_RING_DEPTH = 4;         // cells requested below the one being read
 constexpr u32 CH_FSE_SLOT = FAST_FSE_ENTRIES * 4, CH_HUF_SLOT = FAST_HUF_ENTRIES * 2;
 constexpr u32 CH_OFF_HUF = CH_FSE_WARPS * CH_FSE_LANES * CH_FSE_SLOT;
 constexpr u32 CH_OFF_RING = CH_OFF_HUF + CH_HUF_WARPS * 8 * CH_HUF_SLOT;
-constexpr u32 CH_OFF_CT = CH_OFF_RING + CH_WARPS * 32 * (16 + CH_RING_GROUPS * 16);
+constexpr u32 CH_OFF_LINK = CH_OFF_RING + (CH_HUF_WARPS * 32 + CH_FSE_WARPS * CH_FSE_LANES) * (16 + CH_RING_GROUPS * 16);
+constexpr u32 CH_OFF_CT = CH_OFF_LINK + CH_FSE_WARPS * CH_FSE_LANES * CH_LINK_BYTES;
 constexpr u32 CH_OFF_BAR = CH_OFF_CT + ((sizeof(CodeTables) + 15) / 16) * 16;
 constexpr u32 CH_SMEM = CH_OFF_BAR + (CH_FSE_WARPS * CH_FSE_LANES + CH_HUF_WARPS * 8) * 8;
 
@@ -121,22 +130,42 @@ struct ChainsArgs {
     u32 roles;           // experiments: bit 0 = run the sequence chains, bit 1 = run the Huffman chains (3 = both, the product setting)
 };
 
-__device__ __forceinline__ void chains_fse_warp(const ChainsArgs& a, unsigned char* smem, int warp, int lane) {
+// shared-memory traffic between a walk lane and its value lane (volatile: another warp is on the other side)
+__device__ __forceinline__ u32 lds_v(u32 addr) { u32 v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void sts_v(u32 addr, u32 v) { asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(u32 addr, u32 a, u32 b, u32 c, u32 d) { asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory"); }
+__device__ __forceinline__ void lds_v4(u32 addr, u32& a, u32& b, u32& c, u32& d) { asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory"); }
+// mailbox words behind the ring
+constexpr u32 LK_CONSUMED = CH_LINK_DEPTH * 16, LK_GEN = LK_CONSUMED + 4, LK_NBSEQ = LK_GEN + 4, LK_OUTLO = LK_NBSEQ + 4, LK_OUTHI = LK_OUTLO + 4;
+
+__device__ __forceinline__ void chains_walk_warp(const ChainsArgs& a, unsigned char* smem, int cw, int lane) {
     if (lane >= CH_FSE_LANES) return;
     constexpr u32 MASK = (1u << CH_FSE_LANES) - 1;
-    int const slot = warp * CH_FSE_LANES + lane;
+    int const slot = cw * CH_FSE_LANES + lane;
     u32* const tab = reinterpret_cast<u32*>(smem + (size_t)slot * CH_FSE_SLOT);
     u32 const tabAddr = smem_u32(tab);
-    const CodeTables* const ct = reinterpret_cast<const CodeTables*>(smem + CH_OFF_CT);
     u32 const bar = smem_u32(smem + CH_OFF_BAR + slot * 8);
-    u32 parity = 0;
-    RingWords ws; ws.ring0 = smem_u32(smem + CH_OFF_RING + warp * CH_RING_WARP_BYTES + lane * CH_RING_LANE_BYTES + 16); ws.gIssued = 0;
-    SeqChain D; D.k = D.nbSeq = 0; D.top = 0; D.sLL = D.sOF = D.sML = 0; D.rep0 = D.rep1 = D.rep2 = 1; D.out = nullptr;
+    u32 const link = smem_u32(smem + CH_OFF_LINK + slot * CH_LINK_BYTES);
+    u32 parity = 0, gen = 0, seqNo = 0, consumed = 0;
+    RingWords ws; ws.ring0 = smem_u32(smem + CH_OFF_RING + (CH_HUF_WARPS * 32 + slot) * CH_RING_LANE_BYTES + 16); ws.gIssued = 0;
+    SeqChain D; D.k = D.nbSeq = 0; D.top = 0; D.sLL = D.sOF = D.sML = 0;
     DecDesc* d = nullptr;
-    bool live = false, exhausted = false;
+    bool live = false, exhausted = false, told = false;
+    auto publish = [&](SeqRaw const& r) {
+        sts_v4(link + (seqNo & (CH_LINK_DEPTH - 1)) * 16, r.v0, r.v1, r.a, (r.b & 0x7FFFFFFFu) | ((seqNo << (31 - 4)) & 0x80000000u));      // bit 31: generation of the slot
+        seqNo++;
+    };
+    u32 consumedNext = 0;
     for (;;) {
-        // the common iteration: every lane in the middle of a frame -- one vote, then a straight line
-        if (!__any_sync(MASK, !live || !D.plain())) { D.step_fast(ws, tab, tab + FAST_FSE_OF, tab + FAST_FSE_ML, ct); continue; }
+        // the common iteration: every lane in the middle of a frame with room in its ring -- one vote, then a straight line.
+        // The value lane's progress report is read one iteration ahead of its use (an older report is only more cautious), so
+        // the vote never waits for shared memory.
+        consumed = consumedNext;
+        consumedNext = lds_v(link + LK_CONSUMED);
+        if (!__any_sync(MASK, !live || !D.plain() || seqNo - consumed >= CH_LINK_DEPTH - 3)) {
+            publish(D.walk<true>(ws, tab, tab + FAST_FSE_OF, tab + FAST_FSE_ML));
+            continue;
+        }
         if (!live && !exhausted) {
             u32 item = atomicAdd(a.counterSeq, 1u);
             if (item >= a.n) exhausted = true;
@@ -155,25 +184,89 @@ __device__ __forceinline__ void chains_fse_warp(const ChainsArgs& a, unsigned ch
                     bulk_g2s(tabAddr + FAST_FSE_OF * 4, gt + FAST_FSE_OF, bOF, bar);
                     bulk_g2s(tabAddr + FAST_FSE_ML * 4, gt + FAST_FSE_ML, bML, bar);
                     ws.start(a.srcBase + a.srcOff[item] + d->blockOff + d->seqOff, d->seqBits);
+                    // the value lane must be through with the previous frame before the mailbox changes
+                    while (lds_v(link + LK_CONSUMED) != seqNo) {}
+                    u64 const outp = reinterpret_cast<u64>(a.seqBase + (size_t)item * FAST_MAXS);
+                    sts_v(link + LK_NBSEQ, nbSeq); sts_v(link + LK_OUTLO, (u32)outp); sts_v(link + LK_OUTHI, (u32)(outp >> 32));
+                    __threadfence_block();
+                    sts_v(link + LK_GEN, ++gen);
                     bool const landed = mbar_wait(bar, parity);
                     parity ^= 1;
-                    if (!landed) { d->stC = E_GENERIC; exhausted = true; }
-                    else {
-                        D.begin(ws, ws.g.floorBit, d->seqBits, logLL, logOF, logML, nbSeq, a.seqBase + (size_t)item * FAST_MAXS);
+                    if (!landed) {                           // tell the value lane to skip this frame: it sees fewer records than announced -> send zeros
+                        d->stC = E_GENERIC;
+                        SeqRaw z; z.v0 = z.v1 = z.a = z.b = 0;
+                        for (u32 q = 0; q < nbSeq; q++) { while (seqNo - lds_v(link + LK_CONSUMED) >= CH_LINK_DEPTH - 2) {} publish(z); }
+                    } else {
+                        D.begin(ws, ws.g.floorBit, d->seqBits, logLL, logOF, logML, nbSeq);
                         live = true;
                     }
                 }
             }
         }
+        if (exhausted && !told) {                            // end of work: an empty frame in the mailbox sends the value lane home
+            while (lds_v(link + LK_CONSUMED) != seqNo) {}
+            sts_v(link + LK_NBSEQ, 0u);
+            __threadfence_block();
+            sts_v(link + LK_GEN, ++gen);
+            told = true;
+        }
         if (!__any_sync(MASK, live || !exhausted)) break;
         if (live) {
-            D.step(ws, tab, tab + FAST_FSE_OF, tab + FAST_FSE_ML, ct);
+            while (seqNo - lds_v(link + LK_CONSUMED) >= CH_LINK_DEPTH - 2) {}
+            publish(D.walk<false>(ws, tab, tab + FAST_FSE_OF, tab + FAST_FSE_ML));
             if (!D.more()) { if (!D.clean(ws.g.floorBit)) d->stC = E_corruption_detected; live = false; }
         }
     }
 }
 
-__device__ __forceinline__ void chains_huf_warp(const ChainsArgs& a, unsigned char* smem, int hwarp, int warp, int lane) {
+__device__ __forceinline__ void chains_value_warp(const ChainsArgs& a, unsigned char* smem, int vw, int lane) {
+    (void)a;
+    if (lane >= CH_FSE_LANES) return;
+    constexpr u32 MASK = (1u << CH_FSE_LANES) - 1;
+    int const slot = vw * CH_FSE_LANES + lane;
+    const CodeTables* const ct = reinterpret_cast<const CodeTables*>(smem + CH_OFF_CT);
+    u32 const link = smem_u32(smem + CH_OFF_LINK + slot * CH_LINK_BYTES);
+    SeqValue V; V.begin(nullptr);
+    u32 seen = 0, nb = 0, cons = 0;
+    bool done = false;
+    for (;;) {
+        // the common iteration: every lane inside a frame -- one vote, one ring slot each, no branch on who had news
+        if (!__any_sync(MASK, done || V.k == nb)) {
+            SeqRaw r;
+            lds_v4(link + (cons & (CH_LINK_DEPTH - 1)) * 16, r.v0, r.v1, r.a, r.b);
+            bool const ok = (r.b >> 31) == ((cons >> 4) & 1);
+            V.take_if(ok, r, ct);
+            cons += ok ? 1u : 0u;
+            if (ok && (cons & 3) == 0) sts_v(link + LK_CONSUMED, cons);
+            continue;
+        }
+        if (!done) {
+            if (V.k == nb) {                                 // between frames: report, then look for the next mailbox
+                sts_v(link + LK_CONSUMED, cons);
+                u32 const g = lds_v(link + LK_GEN);
+                if (g != seen) {
+                    __threadfence_block();
+                    nb = lds_v(link + LK_NBSEQ);
+                    u64 const outp = (u64)lds_v(link + LK_OUTLO) | ((u64)lds_v(link + LK_OUTHI) << 32);
+                    V.begin(reinterpret_cast<u64*>(outp));
+                    seen = g;
+                    if (nb == 0) done = true;
+                }
+            } else {
+                SeqRaw r;
+                lds_v4(link + (cons & (CH_LINK_DEPTH - 1)) * 16, r.v0, r.v1, r.a, r.b);
+                if ((r.b >> 31) == ((cons >> 4) & 1)) {      // the record of this turn of the ring has arrived
+                    V.take(r, ct);
+                    cons++;
+                    if ((cons & 3) == 0) sts_v(link + LK_CONSUMED, cons);
+                }
+            }
+        }
+        if (!__any_sync(MASK, !done)) break;
+    }
+}
+
+__device__ __forceinline__ void chains_huf_warp(const ChainsArgs& a, unsigned char* smem, int hwarp, int lane) {
     int const grp = lane >> 2, k = lane & 3;
     u32 const gmask = 0xFu << (lane & ~3);
     int const slot = hwarp * 8 + grp;
@@ -181,7 +274,7 @@ __device__ __forceinline__ void chains_huf_warp(const ChainsArgs& a, unsigned ch
     u32 const tabAddr = smem_u32(tab);
     u32 const bar = smem_u32(smem + CH_OFF_BAR + (CH_FSE_WARPS * CH_FSE_LANES + slot) * 8);
     u32 parity = 0;
-    RingWords ws; ws.ring0 = smem_u32(smem + CH_OFF_RING + warp * CH_RING_WARP_BYTES + lane * CH_RING_LANE_BYTES + 16); ws.gIssued = 0;
+    RingWords ws; ws.ring0 = smem_u32(smem + CH_OFF_RING + (hwarp * 32 + lane) * CH_RING_LANE_BYTES + 16); ws.gIssued = 0;
     HufChain H; H.left = 0; H.op = nullptr; H.kNext = 0; H.hi = H.lo = 0; H.avail = 0; H.budget = 0;
     DecDesc* d = nullptr;
     u32 sh = 0;
@@ -239,9 +332,15 @@ __global__ void __launch_bounds__(CH_WARPS * 32, 1) k_dec_chains(ChainsArgs a) {
         for (int j = 0; j < CH_FSE_WARPS * CH_FSE_LANES + CH_HUF_WARPS * 8; j++) mbar_init(smem_u32(smem + CH_OFF_BAR + j * 8), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // links: every ring slot starts in the "other" generation, mailboxes empty
+    for (u32 j = threadIdx.x; j < CH_FSE_WARPS * CH_FSE_LANES * (CH_LINK_BYTES / 4); j += blockDim.x) {
+        u32 const wIn = j % (CH_LINK_BYTES / 4);
+        reinterpret_cast<u32*>(smem + CH_OFF_LINK)[j] = wIn < CH_LINK_DEPTH * 4 ? 0xFFFFFFFFu : 0u;
+    }
     __syncthreads();
-    if (warp < CH_FSE_WARPS) { if (a.roles & 1) chains_fse_warp(a, smem, warp, lane); }
-    else if (a.roles & 2) chains_huf_warp(a, smem, warp - CH_FSE_WARPS, warp, lane);
+    if (warp < CH_HUF_WARPS) { if (a.roles & 2) chains_huf_warp(a, smem, warp, lane); }
+    else if (warp < CH_HUF_WARPS + CH_FSE_WARPS) { if (a.roles & 1) chains_walk_warp(a, smem, warp - CH_HUF_WARPS, lane); }
+    else if (a.roles & 1) chains_value_warp(a, smem, warp - CH_HUF_WARPS - CH_FSE_WARPS, lane);
 }
 
 }  // namespace zb

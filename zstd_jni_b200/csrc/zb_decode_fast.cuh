@@ -181,16 +181,20 @@ struct MemWords {
 // One step = one sequence, branch free: the next 96 bits of the stream are assembled from four words, the three
 // cells give every bit count, and the three fields of the sequence (offset bits | length bits | state bits) are cut
 // out of that window.  A sequence reads at most 31 + 32 + 26 = 89 bits.
+// The step is cut in two so that, on the GPU, two warps can share it: the WALK (states, bit position: the serial chain proper)
+// hands a 16-byte raw record to the VALUE side (length bases, repcode history, packing, the store), which has no influence on
+// the next state.  A lone warp spends about four cycles per instruction, so halving the chain warp's instructions halves the
+// time of the longest frame.
+struct SeqRaw { u32 v0, v1, a, b; };   // next 64 stream bits at the sequence start | LL cell with the offset's bit count in byte 1 | ML cell
 struct SeqChain {
-    u32 sLL, sOF, sML, rep0, rep1, rep2;
+    u32 sLL, sOF, sML;
     int top;             // bit index of the next unread bit (drops below floorBit on overrun, then reads zeros)
     u32 k, nbSeq;
-    u64* out;
 
     template <class WS>
-    ZB_HD void begin(WS& ws, u32 floorBit, u32 seqBits, u32 logLL, u32 logOF, u32 logML, u32 nbSeq_, u64* out_) {
+    ZB_HD void begin(WS& ws, u32 floorBit, u32 seqBits, u32 logLL, u32 logOF, u32 logML, u32 nbSeq_) {
         top = (int)(floorBit + seqBits) - 1;
-        rep0 = 1; rep1 = 4; rep2 = 8; k = 0; nbSeq = nbSeq_; out = out_;
+        k = 0; nbSeq = nbSeq_;
         u32 W0, W1, W2, W3; ws.fetch4(top >> 5, W0, W1, W2, W3);
         u32 const c = 31u - ((u32)top & 31u);
         u32 const V0 = fshl32(W1, W0, c);
@@ -200,59 +204,76 @@ struct SeqChain {
         top -= (int)t;
         ws.advance(top >> 5);
     }
-    // one sequence; `tLL/tOF/tML` = the frame's three tables (fse2 cells), `ct` = code tables
+    // one sequence; `tLL/tOF/tML` = the frame's three tables (fse2 cells)
     // FAST: the caller guarantees that this is not the frame's last sequence and that the window lies above the stream's first
     // words (no masks); the bitstream request is predicated instead of branched -- a straight line for the warp.
-    template <class WS> ZB_HD void step(WS& ws, const u32* tLL, const u32* tOF, const u32* tML, const CodeTables* ct) { step_t<false>(ws, tLL, tOF, tML, ct); }
-    template <class WS> ZB_HD void step_fast(WS& ws, const u32* tLL, const u32* tOF, const u32* tML, const CodeTables* ct) { step_t<true>(ws, tLL, tOF, tML, ct); }
     template <bool FAST, class WS>
-    ZB_HD void step_t(WS& ws, const u32* tLL, const u32* tOF, const u32* tML, const CodeTables* ct) {
+    ZB_HD SeqRaw walk(WS& ws, const u32* tLL, const u32* tOF, const u32* tML) {
         u32 W0, W1, W2, W3;
         if (FAST) ws.fetch4_fast(top >> 5, W0, W1, W2, W3); else ws.fetch4(top >> 5, W0, W1, W2, W3);
         u32 const c = 31u - ((u32)top & 31u);
         u32 const V0 = fshl32(W1, W0, c), V1 = fshl32(W2, W1, c), V2 = fshl32(W3, W2, c);
         u32 const eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
         u32 const S = eLL + eOF + eML;
-        u32 const ofBits = eOF & 0xFF, llBits = eLL & 0xFF;
-        u32 const q2 = S & 0xFF, E = q2 - ofBits, nTot = (S >> 8) & 0xFF;
+        u32 const q2 = S & 0xFF, nTot = (S >> 8) & 0xFF;
         u32 const nOF = (eOF >> 8) & 0xFF, nML = (eML >> 8) & 0xFF;
         // read order: offset bits, ML extra, LL extra, then LL / ML / OF state bits (ZSTD_decodeSequence :1229-1346)
-        u32 const ofVal = shr_clamp(V0, 32 - ofBits);
-        u32 const x = shr_clamp(fshl32(V1, V0, ofBits), 32 - E);
         bool const far = q2 >= 32;
         u32 const y = shr_clamp(fshl32(far ? V2 : V1, far ? V1 : V0, q2 & 31), 32 - nTot);
         bool const lastSeq = !FAST && (k + 1 == nbSeq);
         top -= (int)(q2 + (lastSeq ? 0u : nTot));
         if (FAST) ws.advance_fast(top >> 5); else ws.advance(top >> 5);      // the next step's four words are requested / waited for while this one finishes
-        u32 const llc = eLL >> 25, mlc = eML >> 25;
-        u32 const litLength = ct->LL_base[llc] + (x & ((1u << llBits) - 1));
-        u32 const matchLength = ct->ML_base[mlc] + (x >> llBits);
-        // offset / repcode history, all cases as selects: idx 0..3 = repcode slots (3: rep0 - 1), 4 = a new offset
-        u32 const ll0 = (llc == 0);          // :1300 tests litLength base == 0, true for code 0 only
-        u32 const idx = ofBits > 1 ? 4u : ofBits + ll0 + ofVal;
-        u32 cand = ((1u << ofBits) - 3) + ofVal;          // selects, not branches: lanes of a warp take all five cases at once
-        cand = idx == 0 ? rep0 : cand; cand = idx == 1 ? rep1 : cand; cand = idx == 2 ? rep2 : cand; cand = idx == 3 ? rep0 - 1 : cand;
-        cand -= !cand;                       // only a repcode can be zero here (rep0 - 1, or a corrupted history)
-        rep2 = idx >= 2 ? rep1 : rep2; rep1 = idx >= 1 ? rep0 : rep1; rep0 = cand;
         sLL = ((eLL >> 16) & 0x1FF) + (y >> (nML + nOF));
         sML = ((eML >> 16) & 0x1FF) + ((y >> nOF) & ((1u << nML) - 1));
         sOF = ((eOF >> 16) & 0x1FF) + (y & ((1u << nOF) - 1));
-        u64 const l = umin(litLength, 0x3FFFFu), m = umin(matchLength, 0x3FFFFu), o = umin(cand, 0xFFFFFFFu);
-        out[k] = l | (m << 18) | (o << 36);
         ++k;
+        SeqRaw r; r.v0 = V0; r.v1 = V1; r.a = (eLL & 0xFFFF00FFu) | ((eOF & 0xFF) << 8); r.b = eML;
+        return r;
     }
     ZB_HD bool more() const { return k < nbSeq; }
-    ZB_HD bool plain() const { return k + 1 < nbSeq && (top >> 5) >= 8; }      // step_fast() may take the next sequence
+    ZB_HD bool plain() const { return k + 1 < nbSeq && (top >> 5) >= 8; }      // walk<true>() may take the next sequence
     ZB_HD bool clean(u32 floorBit) const { return top + 1 == (int)floorBit; }       // every bit consumed, none borrowed
+};
+struct SeqValue {
+    u32 rep0, rep1, rep2, k;
+    u64* out;
+    ZB_HD void begin(u64* out_) { rep0 = 1; rep1 = 4; rep2 = 8; k = 0; out = out_; }
+    ZB_HD void take(SeqRaw const& r, const CodeTables* ct) { take_if(true, r, ct); }
+    // `ok` false: the record was not there yet -- everything is computed, nothing is kept (selects instead of a branch: the value
+    // warp polls 14 rings at once and must not diverge on which of them had news)
+    ZB_HD void take_if(bool ok, SeqRaw const& r, const CodeTables* ct) {
+        u32 const llBits = r.a & 0xFF, ofBits = (r.a >> 8) & 0xFF, mlBits = r.b & 0xFF;
+        u32 const E = llBits + mlBits;
+        u32 const ofVal = shr_clamp(r.v0, 32 - ofBits);
+        u32 const x = shr_clamp(fshl32(r.v1, r.v0, ofBits & 31), 32 - E);
+        u32 const llc = (r.a >> 25) & 0x3F, mlc = (r.b >> 25) & 0x3F;
+        u32 const litLength = ct->LL_base[llc < MaxLL ? llc : MaxLL] + (x & ((1u << (llBits & 31)) - 1));
+        u32 const matchLength = ct->ML_base[mlc < MaxML ? mlc : MaxML] + (x >> (llBits & 31));
+        // offset / repcode history, all cases as selects: idx 0..3 = repcode slots (3: rep0 - 1), 4 = a new offset
+        u32 const ll0 = (llc == 0);          // :1300 tests litLength base == 0, true for code 0 only
+        u32 const idx = ofBits > 1 ? 4u : ofBits + ll0 + ofVal;
+        u32 cand = ((1u << (ofBits & 31)) - 3) + ofVal;   // selects, not branches: lanes of a warp take all five cases at once
+        cand = idx == 0 ? rep0 : cand; cand = idx == 1 ? rep1 : cand; cand = idx == 2 ? rep2 : cand; cand = idx == 3 ? rep0 - 1 : cand;
+        cand -= !cand;                       // only a repcode can be zero here (rep0 - 1, or a corrupted history)
+        u32 const n2 = idx >= 2 ? rep1 : rep2, n1 = idx >= 1 ? rep0 : rep1;
+        rep2 = ok ? n2 : rep2; rep1 = ok ? n1 : rep1; rep0 = ok ? cand : rep0;
+        u64 const l = umin(litLength, 0x3FFFFu), m = umin(matchLength, 0x3FFFFu), o = umin(cand, 0xFFFFFFFu);
+        if (ok) out[k] = l | (m << 18) | (o << 36);
+        k += ok ? 1u : 0u;
+    }
 };
 
 // host / emulator form of stage C for one frame
 ZB_HDN void dec_seq(DecDesc* d, const u8* blk, const u32* fse, const CodeTables* ct, u64* seqOut) {
     if (d->mode != 1 || d->stA1 || d->stA2 || d->nbSeq == 0 || d->seqUnusable) return;
     MemWords ws; ws.g.set(blk + d->seqOff);
-    SeqChain D;
-    D.begin(ws, ws.g.floorBit, d->seqBits, d->logLL, d->logOF, d->logML, d->nbSeq, seqOut);
-    while (D.more()) { if (D.plain()) D.step_fast(ws, fse, fse + FAST_FSE_OF, fse + FAST_FSE_ML, ct); else D.step(ws, fse, fse + FAST_FSE_OF, fse + FAST_FSE_ML, ct); }
+    SeqChain D; SeqValue V;
+    D.begin(ws, ws.g.floorBit, d->seqBits, d->logLL, d->logOF, d->logML, d->nbSeq);
+    V.begin(seqOut);
+    while (D.more()) {
+        SeqRaw const r = D.plain() ? D.walk<true>(ws, fse, fse + FAST_FSE_OF, fse + FAST_FSE_ML) : D.walk<false>(ws, fse, fse + FAST_FSE_OF, fse + FAST_FSE_ML);
+        V.take(r, ct);
+    }
     if (!D.clean(ws.g.floorBit)) d->stC = E_corruption_detected;
 }
 
