@@ -42,4 +42,35 @@ with ZstdBatchContext(0) as b:
     frames = b.compressBatch(chunks[:10], 3)
     assert b.decompressBatch(frames, [len(c) for c in chunks[:10]]) == chunks[:10]
     print("cparams ok", sum(map(len, frames)), flush=True)
+# round 2 additions: streams through the batch layer (direct buffers), the asynchronous begin/end pair, packed (unaligned) outputs
+import io, ctypes as C
+from zstd_jni_b200.zstd import ByteBuffer, ZstdDirectBufferCompressingStream, ZstdDirectBufferDecompressingStream, ZstdOutputStream, ZstdInputStream
+data = b"".join(chunks[:5]) + chunks[9]
+src = ByteBuffer.allocateDirect(len(data)); src.array[:] = np.frombuffer(data, dtype=np.uint8)
+tgt = ByteBuffer.allocateDirect(len(data) + 4096)
+with ZstdDirectBufferCompressingStream(tgt, 3) as zc:
+    zc.compress(src)
+tgt.flip(); back = ByteBuffer.allocateDirect(len(data) + 1)
+zd = ZstdDirectBufferDecompressingStream(tgt)
+while zd.hasRemaining():
+    if zd.read(back) == 0 and not back.hasRemaining(): break
+zd.close()
+assert back.array[: len(data)].tobytes() == data
+sink = io.BytesIO()
+with ZstdOutputStream(sink, 1) as zo:
+    zo.write(data)
+with ZstdInputStream(io.BytesIO(sink.getvalue())) as zi:
+    assert zi.read() == data
+with ZstdBatchContext(0) as b:
+    a = np.frombuffer(b"".join(chunks[:8]), dtype=np.uint8).copy()
+    out = np.empty(a.size + 65536, dtype=np.uint8); sz = (C.c_size_t * 8)()
+    b.compressChunksBegin(0, a, 131072, 3); b.compressChunksBegin(1, a, 131072, 1)
+    t0 = b.compressChunksEnd(0, out, sz); b.compressChunksEnd(1, np.empty(a.size + 65536, dtype=np.uint8))
+    bk = np.empty(a.size, dtype=np.uint8); cap = (C.c_size_t * 8)(*([131072] * 8)); res = (C.c_size_t * 8)()
+    b.decompressFramesBegin(2, out[:t0], sz, bk, cap); b.decompressFramesEnd(2, res)
+    assert (bk == a).all()
+    ragged = [chunks[8], chunks[3][:1001], chunks[10], chunks[5][:77777], chunks[0][:3]]          # packed outputs at odd addresses
+    fr = b.compressBatch(ragged, 3)
+    assert b.decompressBatch(fr, [len(c) for c in ragged]) == ragged
+print("round 2 paths ok", flush=True)
 print("sanitize script done")

@@ -298,7 +298,8 @@ ZB_HD u32 hashSv(u64 d, u32 hBits, u32 mls) {
 // proves the compare would fail, so the candidate bytes -- a random 32-byte HBM sector -- are not fetched at all;
 // decisions are unchanged.  Zero still means "empty".
 constexpr u32 CELL_IDX_MASK = 0x3FFFF;
-ZB_HD u32 tag8(u64 d) { return (u32)((d * 0x9E3779B97F4A7C15ULL) >> 50); }
+// the long table's fingerprint: the 14 bits of the hash product right below the bucket bits (no second multiplication)
+ZB_HD u32 tag8(u64 d, u32 hBits) { return (u32)((d * 0xCF1BBCDCB7A56463ULL) >> (50 - hBits)) & 0x3FFFu; }
 ZB_HD u32 tag4(u32 d) { return (d * 2246822519U) >> 18; }
 ZB_HD u32 cell(u32 idx, u32 tag) { return idx | (tag << 18); }
 
@@ -348,8 +349,10 @@ static ParseStats g_parseStats;
 #define ZB_STAT(x)
 #endif
 
-template <class C>
-ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t srcSize, u32 hBitsL, u32 hBitsS, u32 mls, u32* lastLL) {
+// MLS != 0: the short table's match length is known at compile time (level 3's row has 5), so its hash is one expression, no switch
+template <class C, u32 MLS = 0>
+ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t srcSize, u32 hBitsL, u32 hBitsS, u32 mlsArg, u32* lastLL) {
+    u32 const mls = MLS ? MLS : mlsArg;
     u32* const hashLong = W.hashLong; u32* const hashSmall = W.hashSmall;
     int const n = (int)srcSize, ilimit = n - 8;
     int ip = 1, anchor = 0;
@@ -373,9 +376,10 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             }
             break;
         }
-        u32 width = 1;
+        u32 width;        // smallest power of two >= the estimate, at most the warp
         {   u32 const want = (est4 + 3) / 4;
-            while (width < want && width < (u32)C::W) width *= 2; }
+            width = want <= 1 ? 1u : (1u << (highbit32(want - 1) + 1));
+            if (width > (u32)C::W) width = (u32)C::W; }
         u32 runPos = 0;                   // positions searched in this phase
         int ev = -1;                      // event lane
         // values of the batch that found the event (per lane)
@@ -389,7 +393,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             hl = hash8v(d8, hBitsL);
             u32 const hs = hashSv(d8, hBitsS, mls);
             u32 const tl = active ? ld_probe32(hashLong + hl) : 0, ts = active ? ld_probe32(hashSmall + hs) : 0;
-            u32 const myTagL = tag8(d8), myTagS = tag4((u32)d8);
+            u32 const myTagL = tag8(d8, hBitsL), myTagS = tag4((u32)d8);
             // lane 0 sits at ip: fold the immediate-repcode test into this batch (its load overlaps the table loads)
             bool const rep2Hit = rep2Pending && lane == 0 && off2 > 0 && (load32(src + p - (int)off2) == (u32)d8);
             u32 const mL = w.match_any(active ? hl : (0x80000000u | lane));
@@ -454,7 +458,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
         u32 hl1 = w.shfl(hl, nl), idxl1 = w.shfl(idxl, nl); u64 d81 = w.shfl(d8, nl); bool plaus1 = w.shfl((u32)plausL, nl) != 0;
         if (kinde != 1 && !nextInBatch) {   // position ip1 was not part of the batch: read it now (tables are committed)
             d81 = load64(src + p1e); hl1 = hash8v(d81, hBitsL);
-            u32 const c1 = ld_probe32(hashLong + hl1); idxl1 = c1 & CELL_IDX_MASK; plaus1 = idxl1 >= 2 && (c1 >> 18) == tag8(d81);
+            u32 const c1 = ld_probe32(hashLong + hl1); idxl1 = c1 & CELL_IDX_MASK; plaus1 = idxl1 >= 2 && (c1 >> 18) == tag8(d81, hBitsL);
         }
         u32 mLength, offset = 0; int mpos;
         if (kinde == 1) {
@@ -483,7 +487,7 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
                 ip -= (int)back; mLength += back; }
             off2 = off1; off1 = offset;
             if (lane == 0) {
-                if (ste < 4) hashLong[hl1] = cell((u32)p1e + 2, tag8(d81));
+                if (ste < 4) hashLong[hl1] = cell((u32)p1e + 2, tag8(d81, hBitsL));
                 W.put(nbSeq, (u32)(ip - anchor), offset + 3, mLength);
             }
             nbSeq++;
@@ -493,8 +497,8 @@ ZB_HDN u32 parse_dfast_warp(const C& w, const EncWork& W, const u8* src, size_t 
             if (lane == 0) {   // complementary insertions, in the reference's order (:297-305)
                 u32 const A = (u32)pe + 2;
                 u64 const dA = load64(src + A), dB = load64(src + ip - 2), dC = load64(src + ip - 1);
-                hashLong[hash8v(dA, hBitsL)] = cell(A + 2, tag8(dA));
-                hashLong[hash8v(dB, hBitsL)] = cell((u32)ip - 2 + 2, tag8(dB));
+                hashLong[hash8v(dA, hBitsL)] = cell(A + 2, tag8(dA, hBitsL));
+                hashLong[hash8v(dB, hBitsL)] = cell((u32)ip - 2 + 2, tag8(dB, hBitsL));
                 hashSmall[hashSv(dA, hBitsS, mls)] = cell(A + 2, tag4((u32)dA));
                 hashSmall[hashSv(dC, hBitsS, mls)] = cell((u32)ip - 1 + 2, tag4((u32)dC));
             }
@@ -2109,7 +2113,8 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
         w.sync(); }
     u32 nbSeq = 0, lastLL = 0;
     if (C::W > 1 && (ONLY == S_dfast || (ONLY == 0 && cp.strategy == S_dfast))) {
-        nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
+        if (ONLY == S_dfast && cp.minMatch == 5) nbSeq = parse_dfast_warp<C, 5>(w, W, src, srcSize, cp.hashLog, cp.chainLog, 5, &lastLL);
+        else nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
     } else if (C::W > 1 && (ONLY == S_fast || (ONLY == 0 && cp.strategy == S_fast))) {
         nbSeq = parse_fast_warp(w, W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
     } else if (ONLY == 0 && C::W > 1 && cp.strategy >= S_greedy && cp.strategy <= S_lazy2 && cp.windowLog > 14) {
