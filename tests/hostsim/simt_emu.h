@@ -55,6 +55,7 @@ struct WarpEmuT {
     uint32_t max(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t s = 0; for (int i = 0; i < LANES; i++) if ((uint32_t)all[i] > s) s = (uint32_t)all[i]; return s; }
     uint32_t match_any(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t m = 0; for (int i = 0; i < LANES; i++) if ((uint32_t)all[i] == v) m |= 1u << i; return m; }
     void atomic_inc(uint32_t* p) const { ++*p; }
+    void atomic_add(uint32_t* p, uint32_t v) const { *p += v; }
     uint32_t exscan(uint32_t v) const { const uint64_t* all = exchange(v); uint32_t s = 0; for (int i = 0; i < lane; i++) s += (uint32_t)all[i]; return s; }
     void atomic_or32(uint32_t* p, uint32_t v) const { *p |= v; }
     void atomic_or_byte(uint8_t* p, uint32_t v) const { *p = (uint8_t)(*p | v); }

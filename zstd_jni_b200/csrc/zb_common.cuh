@@ -350,6 +350,7 @@ struct GroupDev {
         return v;
     }
     __device__ __forceinline__ void atomic_inc(u32* p) const { atomicAdd(p, 1u); }
+    __device__ __forceinline__ void atomic_add(u32* p, u32 v) const { atomicAdd(p, v); }
     // exclusive prefix sum over the group's lanes
     __device__ __forceinline__ u32 exscan(u32 v) const {
         u32 x = v;
@@ -377,9 +378,23 @@ struct WarpHost {
     u32 sum(u32 v) const { return v; }
     u32 max(u32 v) const { return v; }
     void atomic_inc(u32* p) const { ++*p; }
+    void atomic_add(u32* p, u32 v) const { *p += v; }
     u32 exscan(u32) const { return 0; }
     void atomic_or32(u32* p, u32 v) const { *p |= v; }
     void atomic_or_byte(u8* p, u32 v) const { *p = (u8)(*p | v); }
 };
+
+// Cooperative copy of n bytes between regions that do not overlap, any alignment on either side: head bytes until dst sits on a
+// 16-byte boundary, then 16 bytes per lane and step (two unaligned 8-byte reads, two aligned 8-byte stores), then the tail.  The
+// aligned reads may touch up to 7 bytes past the source range inside words that also hold requested bytes (see load64).
+template <class C>
+ZB_HD void wcopy(const C& w, u8* dst, const u8* src, size_t n) {
+    size_t head = (size_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15); if (head > n) head = n;
+    for (size_t i = (size_t)w.lane; i < head; i += C::W) dst[i] = src[i];
+    size_t const body = (n - head) / 16;
+    u64* const d8 = reinterpret_cast<u64*>(dst + head); const u8* const s = src + head;
+    for (size_t j = (size_t)w.lane; j < body; j += C::W) { u64 const lo = load64(s + 16 * j), hi = load64(s + 16 * j + 8); d8[2 * j] = lo; d8[2 * j + 1] = hi; }
+    for (size_t i = head + body * 16 + (size_t)w.lane; i < n; i += C::W) dst[i] = src[i];
+}
 
 }  // namespace zb

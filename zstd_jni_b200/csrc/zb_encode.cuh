@@ -982,7 +982,7 @@ ZB_HDN size_t lit_raw(const C& w, u8* dst, size_t cap, const u8* src, size_t n) 
         else if (fl == 2) { u32 const v = (1 << 2) + (u32)(n << 4); dst[0] = (u8)v; dst[1] = (u8)(v >> 8); }
         else { u32 const v = (3 << 2) + (u32)(n << 4); dst[0] = (u8)v; dst[1] = (u8)(v >> 8); dst[2] = (u8)(v >> 16); }
     }
-    for (size_t i = (size_t)w.lane; i < n; i += C::W) dst[fl + i] = src[i];
+    wcopy(w, dst + fl, src, n);
     w.sync();
     return n + fl;
 }
@@ -2207,7 +2207,7 @@ ZB_HDN size_t encode_stage(const C& w, EncShared& S, const EncWork& W, u8* dst, 
     if (cSize == 0) {   // ZSTD_noCompressBlock
         if (srcSize + 3 > cap) return ERR(E_dstSize_tooSmall);
         if (w.lane == 0) { u32 const h = 1 + (u32)(srcSize << 3); op[0] = (u8)h; op[1] = (u8)(h >> 8); op[2] = (u8)(h >> 16); }
-        for (size_t i = (size_t)w.lane; i < srcSize; i += C::W) op[3 + i] = src[i];
+        wcopy(w, op + 3, src, srcSize);
         cSize = srcSize;
     } else if (w.lane == 0) { u32 const h = 1 + (2 << 1) + (u32)(cSize << 3); op[0] = (u8)h; op[1] = (u8)(h >> 8); op[2] = (u8)(h >> 16); }
     if (checksum) {
