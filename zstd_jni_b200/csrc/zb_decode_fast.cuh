@@ -376,8 +376,9 @@ struct alignas(16) ExecRec { u32 o, md, ls, off; };      // output start, match 
 struct ExecShared {
     ExecRec rec[EXEC_G + 1];
     u32 st[EXEC_G + 1 + 64];     // rec[j].o again, then 0xFFFFFFFF: the sorted array the owner searches walk
-    u32 tile[32];                // a round's bytes as far as the first pass produced them ...
-    u32 late[32];                // ... and which of them it did not (bit t of word l: byte t of lane l)
+    u32 tile[32];                // a round's bytes as far as they are known ...
+    u32 late[32];                // ... which of them are not yet (bit t of word l: byte t of lane l) ...
+    u32 link[32];                // ... and, for those, the byte of the round they copy (index inside the round, one byte each)
 };
 // Index (relative to `cur`) of the sequence that holds output position p: the last of st[cur .. cur+63] that is <= p.  A round of
 // 128 bytes holds at most 43 sequence starts and st[cur] <= p for every byte that is looked up, so six halving steps decide.
@@ -535,7 +536,8 @@ ZB_HD size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* it
                 u32 const v = vb + t;
                 ExecRec const r = X.rec[cur + u[t]];
                 bool const isLit = v < r.md;
-                u32 const sv = v - r.off;          // a match that overlaps itself may read `offset` back as long as that byte is final
+                u32 sv = v - r.off;                // a match that overlaps itself may read `offset` back as long as that byte is final;
+                if (!isLit && sv >= floorV && v - r.md >= r.off && r.off) sv = r.md - r.off + exec_mod(v - r.md, r.off);      // if not, its first period holds the same byte
                 srcV[t] = sv;
                 if (isLit) litMask |= 1u << t; else if (sv >= floorV) lateMask |= 1u << t;
                 ad[t] = isLit ? lit + (r.ls + (v - r.o)) : dstA + sv;
@@ -547,29 +549,30 @@ ZB_HD size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* it
                 for (u32 t = 0; t < 4; t++) bt[t] = ((go >> t) & 1) ? (u32)*ad[t] : 0u;
                 if (rle) for (u32 t = 0; t < 4; t++) if ((litMask >> t) & 1) bt[t] = rleByte;
                 val = bt[0] | (bt[1] << 8) | (bt[2] << 16) | (bt[3] << 24); }
-            // second pass, only when some lane needs it: the round's bytes so far go to shared memory, a late byte takes its source from
-            // there unless that one was late too (then it walks the chain itself)
+            // second pass, only when some lane needs it: the round's bytes so far go to shared memory together with, for every byte that
+            // is still missing, the index of the byte it copies.  A missing byte takes its source from there once that one is known;
+            // until then it adopts its source's own link (pointer jumping: chains of copies inside a round -- up to 127 links for an
+            // offset of one -- halve with every turn, so seven turns are the most a round can need)
             if (w.ballot(lateMask != 0)) {
-                X.tile[w.lane] = val; X.late[w.lane] = lateMask;
+                u32 lk = 0;
+                for (u32 t = 0; t < 4; t++) lk |= ((srcV[t] - rb) & 0xFFu) << (8 * t);
+                u32 pend = lateMask;
+                X.tile[w.lane] = val; X.late[w.lane] = pend; X.link[w.lane] = lk;
                 w.sync();
-                for (u32 t = 0; t < 4; t++) {
-                    if (!((lateMask >> t) & 1)) continue;
-                    u32 const j = srcV[t] - rb;                 // byte of the round that is the source
-                    u32 byte;
-                    if (!((X.late[j >> 2] >> (j & 3)) & 1)) byte = (X.tile[j >> 2] >> (8 * (j & 3))) & 0xFF;
-                    else {
-                        u32 v = srcV[t];
-                        for (;;) {
-                            ExecRec const r = X.rec[cur + exec_owner(st, v)];
-                            if (v < r.md) { byte = rle ? rleByte : lit[r.ls + (v - r.o)]; break; }
-                            u32 const k = v - r.md;
-                            v = r.md - r.off + (k < r.off ? k : exec_mod(k, r.off));
-                            if (v < floorV) { byte = dstA[v]; break; }
-                        }
+                for (;;) {
+                    u32 nval = val, npend = pend, nlk = lk;
+                    for (u32 t = 0; t < 4; t++) {
+                        if (!((pend >> t) & 1)) continue;
+                        u32 const j = (lk >> (8 * t)) & 0xFFu;
+                        if (!((X.late[j >> 2] >> (j & 3)) & 1)) { nval |= ((X.tile[j >> 2] >> (8 * (j & 3))) & 0xFFu) << (8 * t); npend &= ~(1u << t); }
+                        else nlk = (nlk & ~(0xFFu << (8 * t))) | (((X.link[j >> 2] >> (8 * (j & 3))) & 0xFFu) << (8 * t));
                     }
-                    val |= byte << (8 * t);
+                    w.sync();                                   // every lane has read the turn's state
+                    val = nval; pend = npend; lk = nlk;
+                    X.tile[w.lane] = val; X.late[w.lane] = pend; X.link[w.lane] = lk;
+                    if (!w.ballot(pend != 0)) break;
+                    w.sync();
                 }
-                w.sync();
             }
             if (validMask == 15) *reinterpret_cast<u32*>(dstA + vb) = val;
             else for (u32 t = 0; t < 4; t++) if ((validMask >> t) & 1) dstA[vb + t] = (u8)(val >> (8 * t));
