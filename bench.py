@@ -327,7 +327,7 @@ def main():
         de(K - 1)
         torch.cuda.synchronize()
     e2e_run(2); barrier()
-    e2e_steps = max(4, min(args.steps, 10))          # the pipeline fills and drains once per run: enough steps to amortise that
+    e2e_steps = max(4, min(args.steps, 32))          # the pipeline fills and drains once per run (~60 ms that no step can hide): the K steps asked for, at least 4
     t0 = time.perf_counter()
     e2e_run(e2e_steps)
     e2e_s = (time.perf_counter() - t0) / e2e_steps

@@ -156,13 +156,14 @@ __device__ __forceinline__ void chains_walk_warp(const ChainsArgs& a, unsigned c
         seqNo++;
     };
     u32 consumedNext = 0;
+    u32 mask = MASK;                    // lanes still at work: a lane that has run out of frames leaves, so that it cannot hold the others on the slow path
     for (;;) {
         // the common iteration: every lane in the middle of a frame with room in its ring -- one vote, then a straight line.
         // The value lane's progress report is read one iteration ahead of its use (an older report is only more cautious), so
         // the vote never waits for shared memory.
         consumed = consumedNext;
         consumedNext = lds_v(link + LK_CONSUMED);
-        if (!__any_sync(MASK, !live || !D.plain() || seqNo - consumed >= CH_LINK_DEPTH - 3)) {
+        if (!__any_sync(mask, !live || !D.plain() || seqNo - consumed >= CH_LINK_DEPTH - 3)) {
             publish(D.walk<true>(ws, tab, tab + FAST_FSE_OF, tab + FAST_FSE_ML));
             continue;
         }
@@ -210,7 +211,10 @@ __device__ __forceinline__ void chains_walk_warp(const ChainsArgs& a, unsigned c
             sts_v(link + LK_GEN, ++gen);
             told = true;
         }
-        if (!__any_sync(MASK, live || !exhausted)) break;
+        {   bool const finished = !live && exhausted;         // (told by now)
+            u32 const gone = __ballot_sync(mask, finished);
+            if (finished) return;
+            mask &= ~gone; }
         if (live) {
             while (seqNo - lds_v(link + LK_CONSUMED) >= CH_LINK_DEPTH - 2) {}
             publish(D.walk<false>(ws, tab, tab + FAST_FSE_OF, tab + FAST_FSE_ML));
@@ -229,9 +233,10 @@ __device__ __forceinline__ void chains_value_warp(const ChainsArgs& a, unsigned 
     SeqValue V; V.begin(nullptr);
     u32 seen = 0, nb = 0, cons = 0;
     bool done = false;
+    u32 mask = MASK;                    // lanes still at work (a lane that was sent home leaves)
     for (;;) {
         // the common iteration: every lane inside a frame -- one vote, one ring slot each, no branch on who had news
-        if (!__any_sync(MASK, done || V.k == nb)) {
+        if (!__any_sync(mask, V.k == nb)) {
             SeqRaw r;
             lds_v4(link + (cons & (CH_LINK_DEPTH - 1)) * 16, r.v0, r.v1, r.a, r.b);
             bool const ok = (r.b >> 31) == ((cons >> 4) & 1);
@@ -262,7 +267,9 @@ __device__ __forceinline__ void chains_value_warp(const ChainsArgs& a, unsigned 
                 }
             }
         }
-        if (!__any_sync(MASK, !done)) break;
+        {   u32 const gone = __ballot_sync(mask, done);
+            if (done) return;
+            mask &= ~gone; }
     }
 }
 
@@ -279,12 +286,15 @@ __device__ __forceinline__ void chains_huf_warp(const ChainsArgs& a, unsigned ch
     DecDesc* d = nullptr;
     u32 sh = 0;
     bool live = false, exhausted = false;
+    u32 mask = 0xFFFFFFFFu;             // groups still at work: a group that has run out of frames leaves, so that it cannot hold the others on the slow path
     for (;;) {
-        if (!__any_sync(0xFFFFFFFFu, !live || !H.plain())) { H.step4_fast(ws, tab, sh); continue; }
-        u32 const liveMask = __ballot_sync(0xFFFFFFFFu, live);
-        u32 const busyMask = __ballot_sync(0xFFFFFFFFu, live || !exhausted);
-        if (!busyMask) break;
-        if ((liveMask & gmask) == 0 && !exhausted) {         // the group's four streams are done: next frame
+        if (!__any_sync(mask, !live || !H.plain())) { H.step4_fast(ws, tab, sh); continue; }
+        u32 const liveMask = __ballot_sync(mask, live);
+        {   bool const finished = (liveMask & gmask) == 0 && exhausted;      // uniform inside a group
+            u32 const gone = __ballot_sync(mask, finished);
+            if (finished) return;
+            mask &= ~gone; }
+        if ((liveMask & gmask) == 0) {                       // the group's four streams are done: next frame
             u32 item = 0xFFFFFFFFu;
             if (k == 0) { item = atomicAdd(a.counterHuf, 1u); item = item < a.n ? a.orderHuf[item] : 0xFFFFFFFFu; }
             item = __shfl_sync(gmask, item, lane & ~3);
@@ -304,7 +314,7 @@ __device__ __forceinline__ void chains_huf_warp(const ChainsArgs& a, unsigned ch
                     u32 const bits = k < (int)d->nStreams ? d->sBits[k] : HUF_UNUSABLE;
                     const u8* const blk = a.srcBase + a.srcOff[item] + d->blockOff;
                     if (bits != HUF_UNUSABLE) ws.start(blk + d->sOff[k], bits);
-                    bool const landed = mbar_wait(bar, parity);
+                    bool const landed = __all_sync(gmask, mbar_wait(bar, parity));      // (one verdict per group)
                     parity ^= 1;
                     if (!landed) { d->stB = E_GENERIC; exhausted = true; }
                     else if (bits != HUF_UNUSABLE) {

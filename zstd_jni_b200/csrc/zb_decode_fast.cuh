@@ -389,7 +389,19 @@ ZB_HD u32 exec_owner(const u32* st, u32 p) {
     return u;
 }
 
-ZB_HD u32 exec_mod(u32 a, u32 b) { return a % b; }
+// a % b for a, b < 2^22 (positions inside a block): on the device through one reciprocal -- the quotient estimate is off by at most
+// one, which two selects repair -- instead of the general 32-bit remainder; b == 0 (records beyond the group) yields garbage, never a trap
+ZB_HD u32 exec_mod(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    u32 const q = (u32)__float2uint_rz(__uint2float_rz(a) * __frcp_rz(__uint2float_rz(b)));
+    u32 r = a - q * b;
+    r = (int)r < 0 ? r + b : r;
+    r = r >= b ? r - b : r;
+    return r;
+#else
+    return b ? a % b : 0;
+#endif
+}
 
 template <class C>
 ZB_HD size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* item, const u8* litBuf, const u64* seqs, u8* dst, size_t cap) {
@@ -532,16 +544,26 @@ ZB_HD size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* it
             // first pass: where every byte comes from; a match folding onto itself reads from its first period.  Bytes whose source is
             // produced in this very round wait for the second pass.
             const u8* ad[4]; u32 srcV[4]; u32 lateMask = 0, litMask = 0;
-            for (u32 t = 0; t < 4; t++) {
-                u32 const v = vb + t;
-                ExecRec const r = X.rec[cur + u[t]];
-                bool const isLit = v < r.md;
-                u32 sv = v - r.off;                // a match that overlaps itself may read `offset` back as long as that byte is final;
-                if (!isLit && sv >= floorV && v - r.md >= r.off && r.off) sv = r.md - r.off + exec_mod(v - r.md, r.off);      // if not, its first period holds the same byte
-                srcV[t] = sv;
-                if (isLit) litMask |= 1u << t; else if (sv >= floorV) lateMask |= 1u << t;
-                ad[t] = isLit ? lit + (r.ls + (v - r.o)) : dstA + sv;
-            }
+            {   u32 rmd[4], roff[4], rlit[4]; u32 foldMask = 0;
+                for (u32 t = 0; t < 4; t++) {
+                    u32 const v = vb + t;
+                    ExecRec const r = X.rec[cur + u[t]];
+                    rmd[t] = r.md; roff[t] = r.off; rlit[t] = r.ls + (v - r.o);
+                    u32 const sv = v - r.off;      // a match that overlaps itself may read `offset` back as long as that byte is final ...
+                    srcV[t] = sv;
+                    if (v < r.md) litMask |= 1u << t;
+                    else if (sv >= floorV && v - r.md >= r.off) foldMask |= 1u << t;
+                }
+                if (w.ballot(foldMask != 0))       // ... if it is not, the match's first period holds the same byte
+                    for (u32 t = 0; t < 4; t++) {
+                        u32 const f = rmd[t] - roff[t] + exec_mod(vb + t - rmd[t], roff[t]);
+                        srcV[t] = ((foldMask >> t) & 1) ? f : srcV[t];
+                    }
+                for (u32 t = 0; t < 4; t++) {
+                    bool const isLit = (litMask >> t) & 1;
+                    if (!isLit && srcV[t] >= floorV) lateMask |= 1u << t;
+                    ad[t] = isLit ? lit + rlit[t] : dstA + srcV[t];
+                } }
             lateMask &= validMask;
             u32 val;
             {   u32 const go = validMask & ~lateMask;
@@ -561,11 +583,13 @@ ZB_HD size_t dec_exec(const C& w, ExecShared& X, const DecDesc* dp, const u8* it
                 w.sync();
                 for (;;) {
                     u32 nval = val, npend = pend, nlk = lk;
-                    for (u32 t = 0; t < 4; t++) {
-                        if (!((pend >> t) & 1)) continue;
-                        u32 const j = (lk >> (8 * t)) & 0xFFu;
-                        if (!((X.late[j >> 2] >> (j & 3)) & 1)) { nval |= ((X.tile[j >> 2] >> (8 * (j & 3))) & 0xFFu) << (8 * t); npend &= ~(1u << t); }
-                        else nlk = (nlk & ~(0xFFu << (8 * t))) | (((X.link[j >> 2] >> (8 * (j & 3))) & 0xFFu) << (8 * t));
+                    for (u32 t = 0; t < 4; t++) {               // straight line: the three words of every byte's source are fetched whether needed or not
+                        u32 const j = (lk >> (8 * t)) & 0x7Fu, jw = j >> 2, js = 8 * (j & 3);
+                        u32 const sLate = (X.late[jw] >> (j & 3)) & 1, sByte = (X.tile[jw] >> js) & 0xFFu, sLink = (X.link[jw] >> js) & 0xFFu;
+                        bool const mine = (pend >> t) & 1, got = mine && !sLate, hop = mine && sLate;
+                        nval |= got ? sByte << (8 * t) : 0u;
+                        npend &= got ? ~(1u << t) : 0xFFFFFFFFu;
+                        nlk = hop ? (nlk & ~(0xFFu << (8 * t))) | (sLink << (8 * t)) : nlk;
                     }
                     w.sync();                                   // every lane has read the turn's state
                     val = nval; pend = npend; lk = nlk;

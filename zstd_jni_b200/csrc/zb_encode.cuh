@@ -1548,6 +1548,7 @@ ZB_HDN u32 parse_fast_warp(const C& w, const EncWork& W, const u8* src, size_t s
 struct RowState {
     u32* hashTable; u8* tagTable; const u8* base;
     u32 hashCache[8];
+    u32 hc;                     // full-warp parsers: lane k (k < 8) holds hashCache[k] in this register instead (a shuffle reads it)
     u32 rowHashLog, rowLog, searchLog, mls, nextToUpdate; bool lazySkipping;
     u32 finder;                 // 0 = hash chain (window <= 2^14), 1 = row based, 2 = binary tree (btlazy2)
     u32* chainTable; u32 hashLog, chainLog;
@@ -1877,6 +1878,51 @@ ZB_HDN u32 parse_lazy(const EncWork& W, const u8* src, size_t srcSize, u32 hashL
 // compare becomes one ballot, every accepted candidate is measured by its own lane, and the winner is the first
 // candidate of maximal length -- which is what the serial loop's "strictly longer replaces" rule selects.  Table
 // writes are made by lane 0 only.
+// The hash cache of a full warp: entry k lives in lane k's register `hc` (no indexed array, hence no local memory), a shuffle reads it;
+// narrower groups keep the array.
+template <class C>
+ZB_HD void row_fill_cache_w(const C& w, RowState& ms, u32 idx, const u8* iLimit) {
+    if (C::W < 32) { row_fill_cache(ms, idx, iLimit); return; }
+    u32 const maxElems = (ms.base + idx) > iLimit ? 0 : (u32)(iLimit - (ms.base + idx) + 1);
+    u32 const lim = idx + (8 < maxElems ? 8 : maxElems);
+    u32 const q = idx + (((u32)w.lane - idx) & 7);              // the position of [idx, idx + 8) whose entry this lane holds
+    if ((u32)w.lane < 8 && q < lim) { u32 const h = row_hash(ms.base + q, ms.rowHashLog + 8, ms.mls); row_prefetch(ms, h); ms.hc = h; }
+}
+template <class C>
+ZB_HD u32 row_next_cached_w(const C& w, RowState& ms, u32 idx) {
+    if (C::W < 32) return row_next_cached(ms, idx);
+    u32 const newHash = row_hash(ms.base + idx + 8, ms.rowHashLog + 8, ms.mls);
+    row_prefetch(ms, newHash);
+    u32 const hash = w.shfl(ms.hc, (int)(idx & 7));
+    if ((u32)w.lane == (idx & 7)) ms.hc = newHash;
+    return hash;
+}
+// Positions [from, to) inserted by a whole warp at once, with the result of inserting them one after the other: lanes that hit the
+// same row find each other with a match-any vote, the r-th of them takes the r-th step of the row's head (head-1, ..., 1, rowMask,
+// ...), the last one leaves the head behind, and where a long run of equal hashes wraps around a row only the latest writer of an
+// entry stores.  One memory round trip per 32 positions instead of one per position.
+template <class C>
+ZB_HD void row_insert_batch(const C& w, RowState& ms, u32 from, u32 to) {
+    u32 const rowMask = (1u << ms.rowLog) - 1;
+    for (u32 b = from; b < to; b += (u32)C::W) {
+        u32 const i = b + (u32)w.lane;
+        bool const active = i < to;
+        u32 const hash = active ? row_hash(ms.base + i, ms.rowHashLog + 8, ms.mls) : 0;
+        u32 const relRow = (hash >> 8) << ms.rowLog;
+        u8* const tagRow = ms.tagTable + relRow;
+        u32 const grp = w.match_any(active ? relRow : (0x80000000u | (u32)w.lane));
+        u32 const rank = popc32(grp & ((1u << w.lane) - 1)), cnt = popc32(grp);
+        u32 h = active ? ((u32)*tagRow & rowMask) : 1u;
+        h = h ? h : 1u;                                        // an empty row's first entry is rowMask, like a head of 1
+        w.sync();                                              // every lane has read its row's head
+        if (active) {
+            u32 const pos = (h + 4 * rowMask - 2 - rank) % rowMask + 1;
+            if (rank + rowMask >= cnt) { tagRow[pos] = (u8)hash; ms.hashTable[relRow + pos] = i; }
+            if (rank + 1 == cnt) *tagRow = (u8)pos;
+        }
+        w.sync();
+    }
+}
 template <class C>
 ZB_HD void row_update_warp(const C& w, RowState& ms, const u8* ip) {
     u32 idx = ms.nextToUpdate;
@@ -1884,7 +1930,7 @@ ZB_HD void row_update_warp(const C& w, RowState& ms, const u8* ip) {
     u32 const rowMask = (1u << ms.rowLog) - 1;
     auto insert_range = [&](u32 from, u32 to) {
         for (u32 i = from; i < to; ++i) {
-            u32 const hash = row_next_cached(ms, i);           // uniform: keeps every lane's cache identical
+            u32 const hash = row_next_cached_w(w, ms, i);     // uniform
             if (w.lane == 0) {
                 u32 const relRow = (hash >> 8) << ms.rowLog;
                 u8* const tagRow = ms.tagTable + relRow;
@@ -1894,36 +1940,63 @@ ZB_HD void row_update_warp(const C& w, RowState& ms, const u8* ip) {
             }
         }
     };
+    if (C::W >= 32 && target - idx > 2) {
+        // the hash cache holds nothing but row_hash() of the next eight positions, so the batch works from the hashes themselves and
+        // the cache is brought to where the serial walk would have left it: positions target .. target + 7
+        if (target - idx > 384) { row_insert_batch(w, ms, idx, idx + 96); idx = target - 32; }
+        row_insert_batch(w, ms, idx, target);
+        {   u32 const q = target + (((u32)w.lane - target) & 7);
+            if ((u32)w.lane < 8) { u32 const h = row_hash(ms.base + q, ms.rowHashLog + 8, ms.mls); row_prefetch(ms, h); ms.hc = h; } }
+        ms.nextToUpdate = target;
+        return;
+    }
     if (target - idx > 384) {
         insert_range(idx, idx + 96);
         idx = target - 32;
-        row_fill_cache(ms, idx, ip + 1);
+        row_fill_cache_w(w, ms, idx, ip + 1);
     }
     insert_range(idx, target);
     ms.nextToUpdate = target;
 }
 template <class C>
-ZB_HDN size_t row_find_best_warp(const C& w, RowState& ms, const u8* ip, const u8* iLimit, size_t* offBasePtr) {
+ZB_HD size_t row_find_best_warp(const C& w, RowState& ms, const u8* ip, const u8* iLimit, size_t* offBasePtr) {
     u32 const curr = (u32)(ip - ms.base);
     u32 const lowLimit = 2;
     u32 const rowEntries = 1u << ms.rowLog, rowMask = rowEntries - 1;
     u32 const maxAttempts = 1u << (ms.searchLog < ms.rowLog ? ms.searchLog : ms.rowLog);
     u32 hash;
-    if (!ms.lazySkipping) { row_update_warp(w, ms, ip); hash = row_next_cached(ms, curr); }
+    if (!ms.lazySkipping) { row_update_warp(w, ms, ip); hash = row_next_cached_w(w, ms, curr); }
     else { hash = row_hash(ip, ms.rowHashLog + 8, ms.mls); ms.nextToUpdate = curr; }
     w.sync();                                              // lane 0's insertions are visible to everybody
     u32 const relRow = (hash >> 8) << ms.rowLog;
     u32 const tag = hash & 0xFF;
     u32* const row = ms.hashTable + relRow;
     u8* const tagRow = ms.tagTable + relRow;
-    u32 const head = *tagRow & rowMask;
+    // a full warp fetches the tag row and the index row in ONE round trip -- lane e holds entries e (and e + 32) -- and the visiting
+    // order (head, head + 1, ... mod rowEntries) is a shuffle; narrower groups walk the rows as the serial code does
+    u32 tb0 = 0, tb1 = 0, ix0 = 0, ix1 = 0;
+    if (C::W >= 32) {
+        if ((u32)w.lane < rowEntries) { tb0 = tagRow[w.lane]; ix0 = row[w.lane]; }
+        if (rowEntries > 32) { tb1 = tagRow[32 + w.lane]; ix1 = row[32 + w.lane]; }
+    }
+    u32 const head = (C::W >= 32 ? w.shfl(tb0, 0) : (u32)*tagRow) & rowMask;
     u32 const ip4 = load32(ip);
     u32 bestLen = 0, bestIdx = 0; bool stopped = false; u32 used = 0;
     for (u32 base = 0; base < rowEntries && !stopped && used < maxAttempts; base += (u32)C::W) {
         u32 const j = base + (u32)w.lane;
         u32 const matchPos = (head + j) & rowMask;
-        bool const hit = j < rowEntries && matchPos != 0 && tagRow[matchPos] == (u8)tag;
-        u32 const idx = hit ? row[matchPos] : 0;
+        bool hit; u32 idx;
+        if (C::W >= 32) {
+            int const from = (int)(matchPos & 31);
+            u32 const t0 = w.shfl(tb0, from), x0 = w.shfl(ix0, from);
+            u32 t = t0, x = x0;
+            if (rowEntries > 32) { u32 const t1 = w.shfl(tb1, from), x1 = w.shfl(ix1, from); if (matchPos >> 5) { t = t1; x = x1; } }
+            hit = j < rowEntries && matchPos != 0 && t == tag;
+            idx = hit ? x : 0;
+        } else {
+            hit = j < rowEntries && matchPos != 0 && tagRow[matchPos] == (u8)tag;
+            idx = hit ? row[matchPos] : 0;
+        }
         u32 const hitMask = w.ballot(hit), staleMask = w.ballot(hit && idx < lowLimit);
         u32 valid = hitMask;
         if (staleMask) { valid &= (1u << ctz32(staleMask)) - 1; stopped = true; }
@@ -1939,9 +2012,9 @@ ZB_HDN size_t row_find_best_warp(const C& w, RowState& ms, const u8* ip, const u
         used += popc32(valid);
     }
     w.sync();
-    if (w.lane == 0) {                                     // "insert current byte into hashtable too"
-        u32 const pos = row_next_index(tagRow, rowMask);
-        tagRow[pos] = (u8)tag;
+    if (w.lane == 0) {                                     // "insert current byte into hashtable too" (row_next_index from the head read above)
+        u32 pos = (head - 1) & rowMask; pos += pos == 0 ? rowMask : 0;
+        tagRow[0] = (u8)pos; tagRow[pos] = (u8)tag;
         row[pos] = ms.nextToUpdate;
     }
     ms.nextToUpdate++;
@@ -1959,66 +2032,68 @@ ZB_HDN u32 parse_lazy_warp(const C& w, const EncWork& W, const u8* src, size_t s
     const u8* const ilimit = useRow ? iend - 8 - 8 : iend - 8;
     const u8* const prefixLowest = src;
     u32 offset_1 = 1, offset_2 = 4, nbSeq = 0;
+    // repcode matches are measured by the whole group (ZSTD_count of two uniform pointers)
+    auto wc = [&](const u8* a, const u8* b) { return (size_t)wcount(w, src, (u32)srcSize, (u32)(a - src), (u32)(b - src)); };
     RowState ms;
     ms.finder = finder; ms.chainTable = W.hashSmall; ms.hashLog = hashLog; ms.chainLog = chainLog;
     ms.hashTable = W.hashLong; ms.tagTable = reinterpret_cast<u8*>(W.hashSmall); ms.base = src - 2;
     ms.mls = minMatch < 4 ? 4 : minMatch > 6 ? 6 : minMatch;
     ms.rowLog = searchLog < 4 ? 4 : searchLog > 6 ? 6 : searchLog;
     ms.searchLog = searchLog; ms.rowHashLog = hashLog - ms.rowLog;
-    ms.nextToUpdate = 2; ms.lazySkipping = false;
+    ms.nextToUpdate = 2; ms.lazySkipping = false; ms.hc = 0;
     ip += 1;
     {   u32 const maxRep = (u32)(ip - prefixLowest);
         if (offset_2 > maxRep) offset_2 = 0;
         if (offset_1 > maxRep) offset_1 = 0; }
-    if (useRow) row_fill_cache(ms, ms.nextToUpdate, ilimit);
+    if (useRow) row_fill_cache_w(w, ms, ms.nextToUpdate, ilimit);
     while (ip < ilimit) {
         size_t matchLength = 0;
         size_t offBase = 1;
         const u8* start = ip + 1;
         bool store = false;
         if ((offset_1 > 0) && (load32(ip + 1 - offset_1) == load32(ip + 1))) {
-            matchLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
+            matchLength = wc(ip + 1 + 4, ip + 1 + 4 - offset_1) + 4;
             if (depth == 0) store = true;
         }
         if (!store) {
-            {   size_t offbaseFound = 999999999;
-                size_t const ml2 = row_find_best_warp(w, ms, ip, iend, &offbaseFound);
-                if (ml2 > matchLength) { matchLength = ml2; start = ip; offBase = offbaseFound; } }
-            if (matchLength < 4) {
+            // The searches at ip, ip + 1 (lazy) and ip + 2 (lazy2) of zstd_lazy.c:1581-1660 as ONE call site in a small state machine
+            // (stage = which of the three is due), so that the finder is inlined once: three copies of it do not fit the
+            // instruction cache next to each other.
+            u32 stage = 0; bool found = true;
+            for (;;) {
+                if (stage) {
+                    ip++;
+                    if ((offBase) && ((offset_1 > 0) && (load32(ip) == load32(ip - offset_1)))) {
+                        size_t const mlRep = wc(ip + 4, ip + 4 - offset_1) + 4;
+                        int const mul = stage == 1 ? 3 : 4;
+                        int const gain2 = (int)(mlRep * mul);
+                        int const gain1 = (int)(matchLength * mul - highbit32((u32)offBase) + 1);
+                        if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
+                    }
+                }
+                size_t ofb = 999999999;
+                size_t const ml2 = row_find_best_warp(w, ms, ip, iend, &ofb);
+                if (stage == 0) {
+                    if (ml2 > matchLength) { matchLength = ml2; start = ip; offBase = ofb; }
+                    if (matchLength < 4) { found = false; break; }
+                    if (depth == 0 || !(ip < ilimit)) break;
+                    stage = 1; continue;
+                }
+                int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofb));
+                int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + (stage == 1 ? 4 : 7));
+                if ((ml2 >= 4) && (gain2 > gain1)) {
+                    matchLength = ml2; offBase = ofb; start = ip;
+                    if (!(ip < ilimit)) break;
+                    stage = 1; continue;
+                }
+                if (stage == 1 && depth == 2 && ip < ilimit) { stage = 2; continue; }
+                break;
+            }
+            if (!found) {
                 size_t const step = ((size_t)(ip - anchor) >> 8) + 1;      // kSearchStrength
                 ip += step;
                 ms.lazySkipping = step > 8;                                // kLazySkippingStep
                 continue;
-            }
-            if (depth >= 1)
-            while (ip < ilimit) {
-                ip++;
-                if ((offBase) && ((offset_1 > 0) && (load32(ip) == load32(ip - offset_1)))) {
-                    size_t const mlRep = count_match(ip + 4, ip + 4 - offset_1, iend) + 4;
-                    int const gain2 = (int)(mlRep * 3);
-                    int const gain1 = (int)(matchLength * 3 - highbit32((u32)offBase) + 1);
-                    if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
-                }
-                {   size_t ofbCandidate = 999999999;
-                    size_t const ml2 = row_find_best_warp(w, ms, ip, iend, &ofbCandidate);
-                    int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofbCandidate));
-                    int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 4);
-                    if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; } }
-                if ((depth == 2) && (ip < ilimit)) {
-                    ip++;
-                    if ((offBase) && ((offset_1 > 0) && (load32(ip) == load32(ip - offset_1)))) {
-                        size_t const mlRep = count_match(ip + 4, ip + 4 - offset_1, iend) + 4;
-                        int const gain2 = (int)(mlRep * 4);
-                        int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 1);
-                        if ((mlRep >= 4) && (gain2 > gain1)) { matchLength = mlRep; offBase = 1; start = ip; }
-                    }
-                    {   size_t ofbCandidate = 999999999;
-                        size_t const ml2 = row_find_best_warp(w, ms, ip, iend, &ofbCandidate);
-                        int const gain2 = (int)(ml2 * 4 - highbit32((u32)ofbCandidate));
-                        int const gain1 = (int)(matchLength * 4 - highbit32((u32)offBase) + 7);
-                        if ((ml2 >= 4) && (gain2 > gain1)) { matchLength = ml2; offBase = ofbCandidate; start = ip; continue; } }
-                }
-                break;
             }
             if (offBase > 3) {   // catch up
                 size_t const off = offBase - 3;
@@ -2029,9 +2104,9 @@ ZB_HDN u32 parse_lazy_warp(const C& w, const EncWork& W, const u8* src, size_t s
         if (w.lane == 0) { W.put(nbSeq, (u32)(start - anchor), (u32)offBase, (u32)matchLength); }
         nbSeq++;
         anchor = ip = start + matchLength;
-        if (ms.lazySkipping) { if (useRow) row_fill_cache(ms, ms.nextToUpdate, ilimit); ms.lazySkipping = false; }
+        if (ms.lazySkipping) { if (useRow) row_fill_cache_w(w, ms, ms.nextToUpdate, ilimit); ms.lazySkipping = false; }
         while (((ip <= ilimit) && (offset_2 > 0)) && (load32(ip) == load32(ip - offset_2))) {
-            matchLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
+            matchLength = wc(ip + 4, ip + 4 - offset_2) + 4;
             u32 const tmp = offset_2; offset_2 = offset_1; offset_1 = tmp;
             if (w.lane == 0) { W.put(nbSeq, 0, 1, (u32)matchLength); }
             nbSeq++;
@@ -2092,13 +2167,15 @@ constexpr u32 FRAME_CHECKSUM = 1, FRAME_NO_CONTENT_SIZE = 2, FRAME_MAGICLESS = 4
 
 // ONLY = 0: every parser is compiled in.  ONLY = S_dfast / S_fast: the caller guarantees that this level selects that
 // strategy for every input size, so the kernel holds a single cooperative parser (64 registers without spills; the
-// all-in-one instantiation needs ~1 KB of stack).
+// all-in-one instantiation needs ~1 KB of stack).  ONLY = ONLY_LAZY: greedy ... btlazy2 for every input size (levels 5 and up):
+// the cooperative row-based parser plus the serial finders, built with its own register budget.
+constexpr u32 ONLY_LAZY = 64;
 template <class C, u32 ONLY = 0>
 ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t srcSize, int level, u32* nbSeqOut, u32* lastLLOut, const CParams* ov = nullptr) {
     CParams cp;
     *nbSeqOut = PARSE_SKIPPED; *lastLLOut = 0;
     if (!get_cparams(&cp, level, srcSize, ov)) return ERR(E_parameter_unsupported);
-    if (ONLY != 0 && cp.strategy != ONLY) return ERR(E_GENERIC);
+    if (ONLY == ONLY_LAZY ? cp.strategy < S_greedy : (ONLY != 0 && cp.strategy != ONLY)) return ERR(E_GENERIC);
     if (srcSize < 7) return 0;
     {   // fresh tables: zero the used part (16-byte stores; the workspace is 16-byte aligned)
         u32 const nL = (1u << cp.hashLog) / 4;
@@ -2117,11 +2194,11 @@ ZB_HDN size_t parse_stage(const C& w, const EncWork& W, const u8* src, size_t sr
         else nbSeq = parse_dfast_warp(w, W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
     } else if (C::W > 1 && (ONLY == S_fast || (ONLY == 0 && cp.strategy == S_fast))) {
         nbSeq = parse_fast_warp(w, W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
-    } else if (ONLY == 0 && C::W > 1 && cp.strategy >= S_greedy && cp.strategy <= S_lazy2 && cp.windowLog > 14) {
+    } else if ((ONLY == 0 || ONLY == ONLY_LAZY) && C::W > 1 && cp.strategy >= S_greedy && cp.strategy <= S_lazy2 && cp.windowLog > 14) {
         nbSeq = parse_lazy_warp(w, W, src, srcSize, cp.hashLog, cp.searchLog, cp.minMatch, cp.strategy - S_greedy, &lastLL);
-    } else if (ONLY == 0) {
+    } else if (ONLY == 0 || ONLY == ONLY_LAZY) {
         if (w.lane == 0) {
-            if (cp.strategy >= S_greedy) nbSeq = parse_lazy(W, src, srcSize, cp.hashLog, cp.chainLog, cp.searchLog, cp.minMatch, cp.strategy == S_btlazy2 ? 2 : cp.strategy - S_greedy,
+            if (ONLY == ONLY_LAZY || cp.strategy >= S_greedy) nbSeq = parse_lazy(W, src, srcSize, cp.hashLog, cp.chainLog, cp.searchLog, cp.minMatch, cp.strategy == S_btlazy2 ? 2 : cp.strategy - S_greedy,
                                                           cp.strategy == S_btlazy2 ? 2u : cp.windowLog > 14 ? 1u : 0u, &lastLL);
             else if (cp.strategy == S_dfast) nbSeq = parse_dfast(W, src, srcSize, cp.hashLog, cp.chainLog, cp.minMatch, &lastLL);
             else nbSeq = parse_fast(W, src, srcSize, cp.hashLog, cp.minMatch, cp.targetLength, &lastLL);
