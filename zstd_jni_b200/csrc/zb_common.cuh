@@ -102,24 +102,49 @@ ZB_HD u32 ld_probe32(const u32* p) {
     return *p;
 #endif
 }
+// Device: from aligned 4-byte words and funnel shifts (three loads and two shifts for eight bytes; the 64-bit form costs two 8-byte
+// loads plus four shifts and the 64-bit arithmetic around them); a word is only touched when it holds a wanted byte.
 ZB_HD u64 load64(const u8* p) {
     uintptr_t const a = reinterpret_cast<uintptr_t>(p);
+#if defined(__CUDA_ARCH__)
+    const u32* const w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    u32 const sh = (u32)(a & 3) * 8;
+    u32 const w0 = w[0], w1 = w[1], w2 = sh ? w[2] : 0u;
+    return (u64)__funnelshift_r(w0, w1, sh) | ((u64)__funnelshift_r(w1, w2, sh) << 32);
+#else
     u32 const sh = (u32)(a & 7) * 8;
     const u8* const A = reinterpret_cast<const u8*>(a & ~(uintptr_t)7);
     u64 const lo = ld_aligned64(A);
     if (sh == 0) return lo;
     return (lo >> sh) | (ld_aligned64(A + 8) << (64 - sh));
+#endif
 }
-// Same, but never touches the second word unless `nbytes` (1..8) needs it.
+// Same, but never touches a word beyond the first `nbytes` (1..8) bytes.
 ZB_HD u64 load64_n(const u8* p, u32 nbytes) {
     uintptr_t const a = reinterpret_cast<uintptr_t>(p);
+#if defined(__CUDA_ARCH__)
+    const u32* const w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    u32 const o = (u32)(a & 3), sh = o * 8;
+    u32 const w0 = w[0], w1 = o + nbytes > 4 ? w[1] : 0u, w2 = o + nbytes > 8 ? w[2] : 0u;
+    return (u64)__funnelshift_r(w0, w1, sh) | ((u64)__funnelshift_r(w1, w2, sh) << 32);
+#else
     u32 const o = (u32)(a & 7);
     const u8* const A = reinterpret_cast<const u8*>(a & ~(uintptr_t)7);
     u64 v = ld_aligned64(A) >> (o * 8);
     if (o + nbytes > 8) v |= ld_aligned64(A + 8) << (64 - o * 8);
     return v;
+#endif
 }
-ZB_HD u32 load32(const u8* p) { return (u32)load64_n(p, 4); }
+ZB_HD u32 load32(const u8* p) {
+#if defined(__CUDA_ARCH__)
+    uintptr_t const a = reinterpret_cast<uintptr_t>(p);
+    const u32* const w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    u32 const sh = (u32)(a & 3) * 8;
+    return __funnelshift_r(w[0], sh ? w[1] : 0u, sh);
+#else
+    return (u32)load64_n(p, 4);
+#endif
+}
 ZB_HD u32 load24(const u8* p) { return (u32)load64_n(p, 3) & 0xFFFFFFu; }
 ZB_HD u32 load16(const u8* p) { return (u32)load64_n(p, 2) & 0xFFFFu; }
 
