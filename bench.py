@@ -432,14 +432,15 @@ def _time_ms(stream, fn, reps=3):
 
 
 def levels_record(args, ctx, L, dev, n, d_src, d_off, d_slots, d_sizes, d_out, d_ooff, stride, st, stream, data, threads, check):
-    """BASELINE.json configs[2] names levels 1 / 3 / 9: compress GB/s of the same 1 GiB, inputs in HBM, CPU arm beside it."""
+    """BASELINE.json configs[2] names levels 1 / 3 / 9: compress GB/s of the same 1 GiB, inputs in HBM, CPU arm beside it (level 5, the
+    first of the lazy family, rides along)."""
     rec = {}
-    for lvl in (1, 9):
+    for lvl in (1, 5, 9):
         def comp():
             check(L.zstdb200_compress_device(ctx.handle, lvl, n, d_src.data_ptr(), d_off.data_ptr(), d_slots.data_ptr(), stride, d_sizes.data_ptr(), st))
             check(L.zstdb200_compact_device(ctx.handle, n, d_slots.data_ptr(), stride, d_sizes.data_ptr(), d_out.data_ptr(), d_ooff.data_ptr(), st))
         ms = _time_ms(stream, comp, reps=2)
-        ncpu = min(n, 1024 if lvl >= 9 else 4096)
+        ncpu = min(n, 1024 if lvl >= 9 else 2048 if lvl >= 5 else 4096)
         cpu = CpuRoundTrip(data[:ncpu], lvl, threads)
         tc, td, cs = cpu.run(); tc, td, cs = cpu.run()
         rec[f"L{lvl}"] = {"compress_gbs": n * CHUNK / (ms * 1e-3) / 1e9, "ms": ms, "cpu_compress_gbs": ncpu * CHUNK / tc / 1e9, "cpu_threads": threads, "cpu_sample_chunks": ncpu}

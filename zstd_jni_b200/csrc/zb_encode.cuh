@@ -1571,7 +1571,7 @@ ZB_HD u32 row_next_index(u8* tagRow, u32 rowMask) {
 // requested while position idx is searched.  Same here, towards L2: tag row (<= 64 B) and index row (<= 256 B).
 ZB_HD void row_prefetch(const RowState& ms, u32 hash) {
     u32 const relRow = (hash >> 8) << ms.rowLog;
-    prefetch_l2(ms.tagTable + relRow);
+    prefetch_l2(ms.tagTable + relRow);            // (towards L1 instead: no gain at level 9, 3 % slower at level 5)
     prefetch_l2(ms.hashTable + relRow);
     if (ms.rowLog == 6) prefetch_l2(ms.hashTable + relRow + 32);
 }
