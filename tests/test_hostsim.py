@@ -166,6 +166,23 @@ def test_randomised_levels_and_sizes():
         assert got == exp, (it, n, level)
 
 
+def test_emulated_row_parser_batches_match_oracle():
+    """The full-warp forms of the row-based finder (levels 5 ... 10): skipped positions inserted 32 at a time -- lanes that hit the same
+    row, rows that wrap inside one batch, the 384-position skip rule -- and rows read in one round trip.  Inputs with long runs of
+    equal hashes and long matches are what reaches those paths."""
+    import numpy as np
+    from zstd_jni_b200 import corpus
+    rng = np.random.default_rng(77)
+    cases = [corpus.chunk(5)[:50000].tobytes(), corpus.chunk(7 + 8 * 2)[:40000].tobytes(), corpus.chunk(0)[:30000].tobytes()]
+    z = np.zeros(50000, dtype=np.uint8); z[rng.integers(0, 50000, 30)] = 9; cases.append(z.tobytes())
+    for per in (3, 33):
+        b = np.tile(rng.integers(0, 256, per, dtype=np.uint8), 40000 // per + 1)[:40000].copy()
+        m = rng.random(40000) < 0.01; b[m] = rng.integers(0, 256, int(m.sum()), dtype=np.uint8); cases.append(b.tobytes())
+    for level in (5, 9, 10):
+        for k, data in enumerate(cases):
+            assert emu_compress(data, level) == oracle_compress(data, level), (level, k)
+
+
 def test_decoders_never_write_outside_their_destination(tmp_path):
     """tests/hostsim/canary_fuzz.cpp: corrupted and intact frames through the fused, emulated-warp and staged decoders; the destination is
     fenced by canaries on both sides (on the GPU the neighbours are other frames' outputs)."""
