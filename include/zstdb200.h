@@ -169,7 +169,13 @@ ZSTDB200_API const char* zstdb200_last_error(void);          /* thread-local tex
 ZSTDB200_API int zstdb200_device_count(void);
 /* tuning knobs (also read from the environment at context creation):
  *   "enc_warps_per_sm" / ZSTDB200_ENC_WARPS_PER_SM, "dec_warps_per_sm" / ZSTDB200_DEC_WARPS_PER_SM,
- *   "parse_lanes" (4|8|16|32), "parse_blocks_per_sm", "dec_pipeline" (0|1), "host_slices", "timing" (0|1) */
+ *   "parse_lanes" (4|8|16|32), "parse_blocks_per_sm", "lazy_blocks_per_sm" (4|6|8: residency of the levels >= 5 parse kernel),
+ *   "parse_est_bytes" (prefix parsed for the cost estimate that orders the parse), "dec_pipeline" (0|1),
+ *   "host_slices" / "host_slices_dec" (slices of the synchronous host-memory calls; defaults 1 / 2), "timing" (0|1),
+ *   "entropy_overlap" (0|1, default 1 / ZSTDB200_ENTROPY_OVERLAP: the entropy stage is launched as a programmatic dependent of the parse and
+ *   takes frames in the order their parse finishes, filling the SMs the parse's tail leaves idle),
+ *   "kernel_fifo" (0|1, default 1 / ZSTDB200_KERNEL_FIFO: the kernel sections of host-memory operations queued on different work sets run
+ *   one after the other in submission order -- copies still overlap them; two batches in the kernels at once only slow each other down) */
 ZSTDB200_API int zstdb200_set_option(zstdb200_ctx* ctx, const char* name, long long value);
 ZSTDB200_API unsigned long long zstdb200_kernel_launches(const zstdb200_ctx* ctx);   /* kernels launched so far */
 /* with option "timing" = 1 every kernel launch is bracketed by CUDA events on its stream; this returns the averages
