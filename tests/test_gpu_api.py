@@ -260,6 +260,36 @@ def test_async_begin_end_api_overlaps_slots():
             ctx.compressChunksEnd(2, outA)                # nothing queued on that slot: stage_wrong
 
 
+def test_overlapped_stages_and_kernel_fifo_keep_the_bytes():
+    """The entropy stage beside the parse (programmatic dependent launch + completion queue) and the one-operation-in-the-kernels rule
+    are scheduling choices: frames are the same bytes with either switched off, for batch sizes around the residency of the parse grid,
+    several levels, and two work sets in flight."""
+    import ctypes as C
+    import numpy as np
+    from zstd_jni_b200 import corpus
+    from zstd_jni_b200.zstd import ZstdBatchContext
+    with ZstdBatchContext(0) as ctx:
+        def both(n, level, start):
+            data = corpus.corpus(n, start=start).reshape(-1)
+            out = []
+            for overlap, fifo in ((1, 1), (0, 1), (1, 0)):
+                ctx.setOption("entropy_overlap", overlap); ctx.setOption("kernel_fifo", fifo)
+                s, f = ctx.compressChunks(data, 131072, level)
+                out.append((s.tobytes(), [int(x) for x in f]))
+            ctx.setOption("entropy_overlap", 1); ctx.setOption("kernel_fifo", 1)
+            return out
+        for n, level, start in ((1, 3, 0), (7, 3, 3), (300, 3, 16), (129, 1, 5), (65, 9, 9), (4800, 3, 0)):
+            a, b, c = both(n, level, start)
+            assert a == b == c, (n, level)
+        # the same batch twice in a row on two work sets: results do not depend on what else is queued
+        data = corpus.corpus(400, start=21).reshape(-1)
+        want, fw = ctx.compressChunks(data, 131072, 3)
+        o0 = np.empty(data.size + 65536, dtype=np.uint8); o1 = np.empty(data.size + 65536, dtype=np.uint8)
+        ctx.compressChunksBegin(0, data, 131072, 3); ctx.compressChunksBegin(1, data, 131072, 3)
+        t0 = ctx.compressChunksEnd(0, o0); t1 = ctx.compressChunksEnd(1, o1)
+        assert o0[:t0].tobytes() == want.tobytes() == o1[:t1].tobytes()
+
+
 def test_input_stream_reads_reference_golden(reference_resources):   # Zstd.scala:426-446
     from zstd_jni_b200.zstd import ZstdInputStream
     xml = (reference_resources / "xml").read_bytes()
