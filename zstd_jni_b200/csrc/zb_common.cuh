@@ -96,7 +96,9 @@ ZB_HD void prefetch_l2(const void* p) {
 #endif
 }
 ZB_HD u32 ld_probe32(const u32* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(ZB_TABLES_MAY_BE_SHARED)
+    return __isShared(p) ? *p : __ldcg(p);          // (experiment: level-1 table in shared memory, k_parse_fast_smem)
+#elif defined(__CUDA_ARCH__)
     return __ldcg(p);
 #else
     return *p;
