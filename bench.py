@@ -13,8 +13,10 @@ scaling); frames are independent so there is no data-path exchange, only an all_
 
 Printed (rank 0, one JSON line): value = uncompressed bytes taken through compress+decompress per second with
 inputs resident in HBM (CUDA events on the launching stream, max over ranks); e2e = the same through the
-host-memory C-ABI calls (pinned host buffers, H2D + kernels + D2H timed); roofline = dominant kernel vs the
-measured HBM peak; cpu_baseline = the reference's own libzstd (oracle/_ref) on this box's host cores.
+host-memory C-ABI calls (pinned host buffers, H2D + kernels + D2H timed); roofline = dominant timed entry vs the
+measured HBM peak -- the two compression stages run overlapped (k_entropy is a programmatic dependent of k_parse), so they
+are ONE entry "k_parse+k_entropy" in kernel_ms; their separate times come from a short serialized pass outside the timed
+region (kernel_ms_serialized); cpu_baseline = the reference's own libzstd (oracle/_ref) on this box's host cores.
 `--impl reference` times only that CPU path with all host threads and prints the same line shape.
 """
 from __future__ import annotations
